@@ -1,0 +1,698 @@
+// PPO update path behind the C ABI: Gaussian-policy / value MLPs (reference ppo.py:38-66), clipped
+// surrogate + value + entropy loss and its gradient (ppo.py:119-144), GAE (utils.py:45-50) and the
+// driver's update block (train.py:171-207).  Everything here is latency-bound (369 505 parameters,
+// minibatches of a few hundred rows): the kernels are small bounds-checked fp32 tile GEMMs, batched
+// over the two trunks (policy / value) so one minibatch step is ~11 launches with no host sync.
+#include "common.cuh"
+#include "elementwise.cuh"
+
+namespace cpb {
+
+namespace {
+
+enum PpoTensor { P_W1, P_B1, P_W2, P_B2, P_WM, P_BM, P_LOGSTD, P_V1, P_VB1, P_V2, P_VB2, P_WV, P_BV, P_COUNT };
+const char* kPpoNames[P_COUNT] = {"dense/kernel", "dense/bias", "dense_1/kernel", "dense_1/bias",
+                                  "action_mean/kernel", "action_mean/bias", "action_logstd",
+                                  "dense_2/kernel", "dense_2/bias", "dense_3/kernel", "dense_3/bias",
+                                  "value/kernel", "value/bias"};
+
+struct PpoLayout {
+    int64_t off[P_COUNT], size[P_COUNT];
+    int32_t shape[P_COUNT][2];
+    int64_t total;
+};
+
+PpoLayout make_ppo_layout(const cpb_ppo_config* c) {
+    PpoLayout L;
+    const int S = c->state_dim, A = c->num_actions, H1 = c->hidden1, H2 = c->hidden2;
+    const int shp[P_COUNT][2] = {{S, H1}, {H1, 0}, {H1, H2}, {H2, 0}, {H2, A}, {A, 0}, {A, 0},
+                                 {S, H1}, {H1, 0}, {H1, H2}, {H2, 0}, {H2, 1}, {1, 0}};
+    int64_t o = 0;
+    for (int i = 0; i < P_COUNT; ++i) {
+        L.shape[i][0] = shp[i][0];
+        L.shape[i][1] = shp[i][1];
+        L.size[i] = (int64_t)shp[i][0] * (shp[i][1] ? shp[i][1] : 1);
+        L.off[i] = o;
+        o += align_up(L.size[i], 64);
+    }
+    L.total = o;
+    return L;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small tile GEMM: C[M,N] (+)= A'[M,K] * B'[K,N], 32x32 tile, 64 threads, 4x4 per thread
+// ---------------------------------------------------------------------------------------------
+constexpr int TS = 32;   // tile edge
+constexpr int TK = 16;   // reduction chunk
+
+// operand access descriptors (element (o, r) = output index o, reduction index r)
+struct Operand {
+    const float* p;
+    long long so, sr;       // strides for the output / reduction index
+    const int32_t* gather;  // optional row gather applied to whichever index has the larger stride
+    int gather_on_o;        // 1: gather indexes o, 0: gather indexes r
+};
+
+__device__ __forceinline__ float fetch(const Operand& a, int o, int r) {
+    long long oo = o, rr = r;
+    if (a.gather != nullptr) {
+        if (a.gather_on_o) oo = a.gather[o];
+        else rr = a.gather[r];
+    }
+    return a.p[oo * a.so + rr * a.sr];
+}
+
+struct GemmJob {
+    Operand a, b;            // a: (m, r), b: (n, r)
+    int M, N, R;
+    float* c;                // [M, ldc]
+    int ldc;
+    const float* bias;       // [N] or null
+    const float* mask;       // [M, ldc] or null: out *= mask > 0
+    int relu;
+    float* colsum;           // [N] or null: colsum[n] = sum_r b(n, r)   (bias gradient; blockIdx.x == 0 only)
+};
+
+struct GemmBatch {
+    GemmJob job[2];
+};
+
+__global__ void __launch_bounds__(64)
+small_gemm_kernel(const __grid_constant__ GemmBatch batch) {
+    const GemmJob& J = batch.job[blockIdx.z];
+    const int m0 = blockIdx.x * TS, n0 = blockIdx.y * TS;
+    if (m0 >= J.M || n0 >= J.N) return;
+    __shared__ __align__(16) float As[TK][TS + 4];
+    __shared__ __align__(16) float Bs[TK][TS + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid & 7, ty = tid >> 3;      // 8 x 8 threads, 4x4 outputs each
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float csum = 0.f;                            // column-sum lane (threads 0..31 own column n0+tid)
+    const bool do_colsum = J.colsum != nullptr && blockIdx.x == 0;
+
+    for (int r0 = 0; r0 < J.R; r0 += TK) {
+        // 512 elements per operand, 8 per thread.  The faster-varying thread index follows the
+        // contiguous memory direction of each operand.
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int f = tid + e * 64;
+            int o, r;
+            if (J.a.so <= J.a.sr) { o = f & 31; r = f >> 5; } else { r = f & 15; o = f >> 4; }
+            As[r][o] = (m0 + o < J.M && r0 + r < J.R) ? fetch(J.a, m0 + o, r0 + r) : 0.f;
+            if (J.b.so <= J.b.sr) { o = f & 31; r = f >> 5; } else { r = f & 15; o = f >> 4; }
+            Bs[r][o] = (n0 + o < J.N && r0 + r < J.R) ? fetch(J.b, n0 + o, r0 + r) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < TK; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w};
+            const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (do_colsum && tid < 32) {
+#pragma unroll
+            for (int k = 0; k < TK; ++k) csum += Bs[k][tid];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= J.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= J.N) continue;
+            float v = acc[i][j] + (J.bias ? J.bias[n] : 0.f);
+            if (J.relu) v = fmaxf(v, 0.f);
+            if (J.mask) v = J.mask[(long long)m * J.ldc + n] > 0.f ? v : 0.f;
+            J.c[(long long)m * J.ldc + n] = v;
+        }
+    }
+    if (do_colsum && tid < 32 && n0 + tid < J.N) J.colsum[n0 + tid] = csum;
+}
+
+int32_t launch_small_gemm(const GemmBatch& b, int njobs, cudaStream_t s) {
+    int maxM = 0, maxN = 0;
+    for (int i = 0; i < njobs; ++i) {
+        if (b.job[i].M > maxM) maxM = b.job[i].M;
+        if (b.job[i].N > maxN) maxN = b.job[i].N;
+    }
+    if (maxM == 0 || maxN == 0) return CPB_OK;
+    dim3 grid(cdiv(maxM, TS), cdiv(maxN, TS), njobs);
+    small_gemm_kernel<<<grid, 64, 0, s>>>(b);
+    CPB_LAUNCHED();
+    return CPB_OK;
+}
+
+// Y[B,N] = act(X[B,K] W[K,N] + b)
+GemmJob fwd_job(const float* x, const int32_t* idx, int B, int K, const float* w, int N, const float* bias,
+                float* y, int relu) {
+    GemmJob j;
+    memset(&j, 0, sizeof(j));
+    j.a = Operand{x, K, 1, idx, 1};
+    j.b = Operand{w, 1, N, nullptr, 0};
+    j.M = B; j.N = N; j.R = K; j.c = y; j.ldc = N; j.bias = bias; j.relu = relu;
+    return j;
+}
+// dX[B,K] = (dY[B,N] W[K,N]^T) * (H > 0)
+GemmJob bwd_data_job(const float* dy, int B, int N, const float* w, int K, const float* h, float* dx) {
+    GemmJob j;
+    memset(&j, 0, sizeof(j));
+    j.a = Operand{dy, N, 1, nullptr, 0};
+    j.b = Operand{w, N, 1, nullptr, 0};       // b(k, n) = W[k*N + n]
+    j.M = B; j.N = K; j.R = N; j.c = dx; j.ldc = K; j.mask = h;
+    return j;
+}
+// gW[K,N] = X[B,K]^T dY[B,N];  gb[N] = colsum(dY)
+GemmJob bwd_weight_job(const float* x, const int32_t* idx, int B, int K, const float* dy, int N, float* gw, float* gb) {
+    GemmJob j;
+    memset(&j, 0, sizeof(j));
+    j.a = Operand{x, 1, K, idx, 0};           // a(k, b) = X[b*K + k]
+    j.b = Operand{dy, 1, N, nullptr, 0};      // b(n, b) = dY[b*N + n]
+    j.M = K; j.N = N; j.R = B; j.c = gw; j.ldc = N; j.colsum = gb;
+    return j;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-sample head: action mean, value, log-prob, ratio, losses and the gradients w.r.t. the two
+// 300-wide trunk outputs.  One warp per sample.
+// ---------------------------------------------------------------------------------------------
+constexpr float kLogSqrt2Pi = 0.9189385175704956f;
+constexpr float kEntropyConst = 1.4189385175704956f;
+constexpr int kMaxActions = 4;
+
+struct HeadArgs {
+    const float* h2;       // [B,H2] policy trunk output (post-relu)
+    const float* g2;       // [B,H2] value trunk output (post-relu), may be null (old policy)
+    const float* wm; const float* bm; const float* logstd;   // action head
+    const float* wv; const float* bv;                        // value head
+    const float* actions; const float* returns; const float* adv;   // [T,A], [T], [T] (gathered through idx)
+    const int32_t* idx;
+    const float* logp_old_in;   // [T] gathered through idx (learn path) or [B] ungathered (train_step path)
+    int logp_old_gathered;
+    int B, H2, A;
+    float low[kMaxActions], high[kMaxActions];
+    float eps_clip, value_scale, entropy_scale;
+    // outputs
+    float* logp_out;       // [B] (old-policy pass: log-prob only)
+    float* mu_out;         // [B,A] or null
+    float* v_out;          // [B] or null
+    float* dpre;           // [B,A] gradient w.r.t. the action head pre-activation
+    float* dv;             // [B]   gradient w.r.t. the value output
+    float* dh2;            // [B,H2] masked gradient w.r.t. policy trunk output
+    float* dg2;            // [B,H2] masked gradient w.r.t. value trunk output
+    float* partial;        // [nblocks][8]: policy, value, ratio sums, logstd grads...
+    const float* noise;    // predict path: [B,A] or null
+    float* action_out;     // predict path
+};
+
+// mode 0: log-prob only (old policy); mode 1: full training head; mode 2: predict (mu / sampled action, value)
+template <int MODE>
+__global__ void __launch_bounds__(256)
+ppo_head_kernel(const __grid_constant__ HeadArgs a) {
+    __shared__ float red[8][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 8 + warp;
+    float vals[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (b < a.B) {
+        const float* h = a.h2 + (long long)b * a.H2;
+        float pre[kMaxActions] = {0.f, 0.f, 0.f, 0.f};
+        float vsum = 0.f;
+        for (int j = lane; j < a.H2; j += 32) {
+            const float hv = h[j];
+#pragma unroll
+            for (int k = 0; k < kMaxActions; ++k)
+                if (k < a.A) pre[k] = fmaf(hv, a.wm[j * a.A + k], pre[k]);
+            if (MODE != 0) vsum = fmaf(a.g2[(long long)b * a.H2 + j], a.wv[j], vsum);
+        }
+#pragma unroll
+        for (int k = 0; k < kMaxActions; ++k) pre[k] = warp_sum(pre[k]);
+        if (MODE != 0) vsum = warp_sum(vsum);
+        const int row = a.idx != nullptr ? a.idx[b] : b;
+        float t[kMaxActions], mu[kMaxActions], diff[kMaxActions], sigma[kMaxActions];
+        float logp = 0.f;
+#pragma unroll
+        for (int k = 0; k < kMaxActions; ++k) {
+            if (k >= a.A) continue;
+            t[k] = tanhf(pre[k] + a.bm[k]);
+            mu[k] = a.low[k] + ((t[k] + 1.f) * 0.5f) * (a.high[k] - a.low[k]);
+            sigma[k] = expf(a.logstd[k]);
+            if (MODE != 2) {
+                diff[k] = (a.actions[(long long)row * a.A + k] - mu[k]) / sigma[k];
+                logp += -0.5f * diff[k] * diff[k] - (kLogSqrt2Pi + a.logstd[k]);
+            }
+        }
+        if (MODE == 0) {
+            if (lane == 0) a.logp_out[b] = logp;
+        } else if (MODE == 2) {
+            const float v = vsum + a.bv[0];
+            if (lane == 0) {
+                a.v_out[b] = v;
+#pragma unroll
+                for (int k = 0; k < kMaxActions; ++k) {
+                    if (k >= a.A) continue;
+                    float act = mu[k];
+                    if (a.noise != nullptr) act = fminf(fmaxf(fmaf(a.noise[(long long)b * a.A + k], sigma[k], mu[k]), a.low[k]), a.high[k]);
+                    a.action_out[(long long)b * a.A + k] = act;
+                }
+            }
+        } else {
+            const float v = vsum + a.bv[0];
+            const float logp_old = a.logp_old_in[a.logp_old_gathered ? row : b];
+            const float ratio = expf(logp - logp_old);
+            const float adv = a.adv[row], ret = a.returns[row];
+            const float unclipped = ratio * adv;
+            const float clipped = fminf(fmaxf(ratio, 1.f - a.eps_clip), 1.f + a.eps_clip) * adv;
+            const float inv_b = 1.f / (float)a.B;
+            // d(-mean(min(u, c)))/d ratio: tf.minimum routes to u when u <= c; the clipped branch has
+            // zero slope outside the clip range (inside it u == c and the first branch is taken).
+            const float dratio = unclipped <= clipped ? -adv * inv_b : 0.f;
+            const float dlogp = dratio * ratio;
+            const float dvv = a.value_scale * 2.f * inv_b * (v - ret);
+            float dp[kMaxActions] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < kMaxActions; ++k) {
+                if (k >= a.A) continue;
+                const float dmu = dlogp * diff[k] / sigma[k];
+                dp[k] = dmu * 0.5f * (a.high[k] - a.low[k]) * (1.f - t[k] * t[k]);
+            }
+            if (lane == 0) {
+                a.dv[b] = dvv;
+#pragma unroll
+                for (int k = 0; k < kMaxActions; ++k)
+                    if (k < a.A) a.dpre[(long long)b * a.A + k] = dp[k];
+                if (a.mu_out != nullptr)
+#pragma unroll
+                    for (int k = 0; k < kMaxActions; ++k)
+                        if (k < a.A) a.mu_out[(long long)b * a.A + k] = mu[k];
+                if (a.v_out != nullptr) a.v_out[b] = v;
+            }
+            for (int j = lane; j < a.H2; j += 32) {
+                float s = 0.f;
+#pragma unroll
+                for (int k = 0; k < kMaxActions; ++k)
+                    if (k < a.A) s = fmaf(dp[k], a.wm[j * a.A + k], s);
+                a.dh2[(long long)b * a.H2 + j] = h[j] > 0.f ? s : 0.f;
+                a.dg2[(long long)b * a.H2 + j] = a.g2[(long long)b * a.H2 + j] > 0.f ? dvv * a.wv[j] : 0.f;
+            }
+            vals[0] = fminf(unclipped, clipped);
+            vals[1] = (v - ret) * (v - ret);
+            vals[2] = ratio;
+#pragma unroll
+            for (int k = 0; k < kMaxActions; ++k)
+                if (k < a.A) vals[3 + k] = dlogp * (diff[k] * diff[k] - 1.f);
+        }
+    }
+    if (MODE == 1) {
+        if (lane == 0)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) red[warp][k] = vals[k];
+        __syncthreads();
+        if (threadIdx.x < 8) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+            a.partial[blockIdx.x * 8 + threadIdx.x] = s;
+        }
+    }
+}
+
+// metrics[5] = policy_loss, value_loss, entropy_loss, loss, mean ratio; grads[logstd], value-bias etc.
+__global__ void ppo_finalize_kernel(const float* __restrict__ partial, int nblocks, int B, int A,
+                                    const float* __restrict__ logstd, float value_scale, float entropy_scale,
+                                    float* __restrict__ glogstd, float* __restrict__ metrics) {
+    __shared__ float tot[8];
+    if (threadIdx.x < 8) {
+        float s = 0.f;
+        for (int i = 0; i < nblocks; ++i) s += partial[i * 8 + threadIdx.x];
+        tot[threadIdx.x] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const float inv_b = 1.f / (float)B;
+        float ent = 0.f;
+        for (int k = 0; k < A; ++k) {
+            ent += kEntropyConst + logstd[k];
+            glogstd[k] = tot[3 + k] - entropy_scale;
+        }
+        const float pl = tot[0] * inv_b;
+        const float vl = tot[1] * inv_b * value_scale;
+        const float el = ent * entropy_scale;
+        if (metrics != nullptr) {
+            metrics[0] = pl; metrics[1] = vl; metrics[2] = el; metrics[3] = -pl + vl - el; metrics[4] = tot[2] * inv_b;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GAE: backward affine scan in float64, one CTA
+// ---------------------------------------------------------------------------------------------
+struct Affine { double a, b; };   // y -> a*y + b
+__device__ __forceinline__ Affine compose(const Affine& first, const Affine& second) {
+    return Affine{first.a * second.a, first.b * second.a + second.b};   // second(first(y))
+}
+
+__global__ void __launch_bounds__(1024)
+gae_kernel(const double* __restrict__ rewards, const double* __restrict__ values, double bootstrap,
+           const double* __restrict__ dones, int T, double gamma, double lam, double* __restrict__ adv_out,
+           double* __restrict__ ret_out, double* __restrict__ advn_out, float* __restrict__ ret32,
+           float* __restrict__ advn32, double* __restrict__ scratch /* [T] when adv_out is null */) {
+    __shared__ Affine warp_tot[32];
+    __shared__ double carry_s;
+    __shared__ double red[32];
+    double* adv = adv_out != nullptr ? adv_out : scratch;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double c = gamma * lam;
+    if (tid == 0) carry_s = 0.0;
+    __syncthreads();
+    // u = reversed time index: y[u] = delta[u] + c*y[u-1]
+    for (int base = 0; base < T; base += 1024) {
+        const int u = base + tid;
+        Affine f{1.0, 0.0};
+        if (u < T) {
+            const int t = T - 1 - u;
+            const double vnext = t + 1 < T ? values[t + 1] : bootstrap;
+            const double delta = rewards[t] + (1.0 - dones[t]) * gamma * vnext - values[t];
+            f = Affine{c, delta};
+        }
+        // inclusive warp scan (composition order: earlier u first)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double pa = __shfl_up_sync(0xffffffffu, f.a, o);
+            const double pb = __shfl_up_sync(0xffffffffu, f.b, o);
+            if (lane >= o) f = compose(Affine{pa, pb}, f);
+        }
+        if (lane == 31) warp_tot[warp] = f;
+        __syncthreads();
+        if (warp == 0) {
+            Affine g = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double pa = __shfl_up_sync(0xffffffffu, g.a, o);
+                const double pb = __shfl_up_sync(0xffffffffu, g.b, o);
+                if (lane >= o) g = compose(Affine{pa, pb}, g);
+            }
+            warp_tot[lane] = g;
+        }
+        __syncthreads();
+        if (warp > 0) f = compose(warp_tot[warp - 1], f);
+        const double carry = carry_s;
+        const double y = f.a * carry + f.b;
+        if (u < T) adv[T - 1 - u] = y;
+        __syncthreads();
+        if (tid == 1023) carry_s = y;
+        __syncthreads();
+    }
+    // mean / population std (numpy: mean, then mean of squared deviations)
+    double s = 0.0;
+    for (int i = tid; i < T; i += 1024) s += adv[i];
+    s = warp_sum(s);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+        double t = red[lane];
+        t = warp_sum(t);
+        if (lane == 0) red[0] = t;
+    }
+    __syncthreads();
+    const double mean = red[0] / T;
+    __syncthreads();
+    double q = 0.0;
+    for (int i = tid; i < T; i += 1024) { const double d = adv[i] - mean; q += d * d; }
+    q = warp_sum(q);
+    if (lane == 0) red[warp] = q;
+    __syncthreads();
+    if (warp == 0) {
+        double t = red[lane];
+        t = warp_sum(t);
+        if (lane == 0) red[0] = t;
+    }
+    __syncthreads();
+    const double sd = sqrt(red[0] / T);
+    for (int i = tid; i < T; i += 1024) {
+        const double a = adv[i];
+        const double r = a + values[i];
+        const double an = (a - mean) / (sd + 1e-8);
+        if (ret_out != nullptr) ret_out[i] = r;
+        if (advn_out != nullptr) advn_out[i] = an;
+        if (ret32 != nullptr) ret32[i] = (float)r;
+        if (advn32 != nullptr) advn32[i] = (float)an;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace plan
+// ---------------------------------------------------------------------------------------------
+struct PpoPlan {
+    float *h1, *h2;        // [2][B,H1], [2][B,H2]  (policy trunk, value trunk)
+    float *dh2, *dh1;      // same shapes
+    float *oh1, *oh2;      // old-policy trunk [rows,H1], [rows,H2]
+    float *logp_old;       // [rows]
+    float *dpre, *dv, *partial;
+    float *ret32, *adv32;  // [T]
+    double* gae_scratch;   // [T]
+    int64_t bytes;
+    bool ok;
+};
+
+PpoPlan make_ppo_plan(void* ws, int64_t ws_bytes, const cpb_ppo_config* c, int max_batch, int horizon) {
+    PpoPlan p;
+    memset(&p, 0, sizeof(p));
+    Arena a(ws, ws_bytes);
+    const int64_t B = max_batch, H1 = c->hidden1, H2 = c->hidden2;
+    const int64_t rows = horizon > max_batch ? horizon : max_batch;
+    p.h1 = a.take<float>(2 * B * H1);
+    p.h2 = a.take<float>(2 * B * H2);
+    p.dh2 = a.take<float>(2 * B * H2);
+    p.dh1 = a.take<float>(2 * B * H1);
+    p.oh1 = a.take<float>(rows * H1);
+    p.oh2 = a.take<float>(rows * H2);
+    p.logp_old = a.take<float>(rows);
+    p.dpre = a.take<float>(B * kMaxActions);
+    p.dv = a.take<float>(B);
+    p.partial = a.take<float>((int64_t)cdiv(B, 8) * 8);
+    p.ret32 = a.take<float>(rows);
+    p.adv32 = a.take<float>(rows);
+    p.gae_scratch = a.take<double>(rows);
+    p.bytes = a.off;
+    p.ok = ws == nullptr || !a.overflow;
+    return p;
+}
+
+int32_t check_ppo_cfg(const cpb_ppo_config* c) {
+    CPB_REQUIRE(c != nullptr, "ppo cfg is NULL");
+    CPB_REQUIRE(c->state_dim >= 1 && c->hidden1 >= 1 && c->hidden2 >= 1, "ppo: bad layer sizes");
+    CPB_REQUIRE(c->num_actions >= 1 && c->num_actions <= kMaxActions, "ppo: num_actions must be in [1,%d]", kMaxActions);
+    return CPB_OK;
+}
+
+HeadArgs head_args(const cpb_ppo_config* c, const PpoLayout& L, const float* params, int B) {
+    HeadArgs h;
+    memset(&h, 0, sizeof(h));
+    h.wm = params + L.off[P_WM]; h.bm = params + L.off[P_BM]; h.logstd = params + L.off[P_LOGSTD];
+    h.wv = params + L.off[P_WV]; h.bv = params + L.off[P_BV];
+    h.B = B; h.H2 = c->hidden2; h.A = c->num_actions;
+    for (int k = 0; k < kMaxActions; ++k) { h.low[k] = c->action_low[k]; h.high[k] = c->action_high[k]; }
+    h.eps_clip = c->epsilon; h.value_scale = c->value_scale; h.entropy_scale = c->entropy_scale;
+    return h;
+}
+
+// log pi_old(a|s) for `rows` samples (optionally gathered)
+int32_t run_old_logp(const cpb_ppo_config* c, const PpoLayout& L, const PpoPlan& pl, const float* params_old,
+                     const float* states, const float* actions, const int32_t* idx, int rows, cudaStream_t s) {
+    GemmBatch gb;
+    gb.job[0] = fwd_job(states, idx, rows, c->state_dim, params_old + L.off[P_W1], c->hidden1, params_old + L.off[P_B1], pl.oh1, 1);
+    CPB_TRY(launch_small_gemm(gb, 1, s));
+    gb.job[0] = fwd_job(pl.oh1, nullptr, rows, c->hidden1, params_old + L.off[P_W2], c->hidden2, params_old + L.off[P_B2], pl.oh2, 1);
+    CPB_TRY(launch_small_gemm(gb, 1, s));
+    HeadArgs h = head_args(c, L, params_old, rows);
+    h.h2 = pl.oh2; h.actions = actions; h.idx = idx; h.logp_out = pl.logp_old;
+    ppo_head_kernel<0><<<cdiv(rows, 8), 256, 0, s>>>(h);
+    CPB_LAUNCHED();
+    return CPB_OK;
+}
+
+int32_t run_trunks(const cpb_ppo_config* c, const PpoLayout& L, const PpoPlan& pl, const float* params,
+                   const float* states, const int32_t* idx, int B, cudaStream_t s) {
+    const int S = c->state_dim, H1 = c->hidden1, H2 = c->hidden2;
+    GemmBatch gb;
+    gb.job[0] = fwd_job(states, idx, B, S, params + L.off[P_W1], H1, params + L.off[P_B1], pl.h1, 1);
+    gb.job[1] = fwd_job(states, idx, B, S, params + L.off[P_V1], H1, params + L.off[P_VB1], pl.h1 + (long long)B * H1, 1);
+    CPB_TRY(launch_small_gemm(gb, 2, s));
+    gb.job[0] = fwd_job(pl.h1, nullptr, B, H1, params + L.off[P_W2], H2, params + L.off[P_B2], pl.h2, 1);
+    gb.job[1] = fwd_job(pl.h1 + (long long)B * H1, nullptr, B, H1, params + L.off[P_V2], H2, params + L.off[P_VB2],
+                        pl.h2 + (long long)B * H2, 1);
+    return launch_small_gemm(gb, 2, s);
+}
+
+// forward + loss + gradients for one minibatch; logp_old given (gathered or not)
+int32_t run_loss_grad(const cpb_ppo_config* c, const PpoLayout& L, const PpoPlan& pl, const float* params,
+                      const float* states, const float* actions, const float* returns, const float* adv,
+                      const int32_t* idx, int B, const float* logp_old, int logp_old_gathered, float* grads,
+                      float* metrics, cudaStream_t s) {
+    const int S = c->state_dim, H1 = c->hidden1, H2 = c->hidden2, A = c->num_actions;
+    CPB_TRY(run_trunks(c, L, pl, params, states, idx, B, s));
+    float* h1p = pl.h1; float* h1v = pl.h1 + (long long)B * H1;
+    float* h2p = pl.h2; float* h2v = pl.h2 + (long long)B * H2;
+    float* dh2p = pl.dh2; float* dh2v = pl.dh2 + (long long)B * H2;
+    float* dh1p = pl.dh1; float* dh1v = pl.dh1 + (long long)B * H1;
+    HeadArgs h = head_args(c, L, params, B);
+    h.h2 = h2p; h.g2 = h2v; h.actions = actions; h.returns = returns; h.adv = adv; h.idx = idx;
+    h.logp_old_in = logp_old; h.logp_old_gathered = logp_old_gathered;
+    h.dpre = pl.dpre; h.dv = pl.dv; h.dh2 = dh2p; h.dg2 = dh2v; h.partial = pl.partial;
+    const int nblocks = cdiv(B, 8);
+    ppo_head_kernel<1><<<nblocks, 256, 0, s>>>(h);
+    CPB_LAUNCHED();
+    ppo_finalize_kernel<<<1, 32, 0, s>>>(pl.partial, nblocks, B, A, params + L.off[P_LOGSTD], c->value_scale,
+                                         c->entropy_scale, grads + L.off[P_LOGSTD], metrics);
+    CPB_LAUNCHED();
+    GemmBatch gb;
+    // head weights: gWm[H2,A] = h2p^T dpre, gbm = colsum(dpre); gWv[H2,1] = h2v^T dv, gbv = sum(dv)
+    gb.job[0] = bwd_weight_job(h2p, nullptr, B, H2, pl.dpre, A, grads + L.off[P_WM], grads + L.off[P_BM]);
+    gb.job[1] = bwd_weight_job(h2v, nullptr, B, H2, pl.dv, 1, grads + L.off[P_WV], grads + L.off[P_BV]);
+    CPB_TRY(launch_small_gemm(gb, 2, s));
+    // layer 2 of both trunks
+    gb.job[0] = bwd_weight_job(h1p, nullptr, B, H1, dh2p, H2, grads + L.off[P_W2], grads + L.off[P_B2]);
+    gb.job[1] = bwd_weight_job(h1v, nullptr, B, H1, dh2v, H2, grads + L.off[P_V2], grads + L.off[P_VB2]);
+    CPB_TRY(launch_small_gemm(gb, 2, s));
+    gb.job[0] = bwd_data_job(dh2p, B, H2, params + L.off[P_W2], H1, h1p, dh1p);
+    gb.job[1] = bwd_data_job(dh2v, B, H2, params + L.off[P_V2], H1, h1v, dh1v);
+    CPB_TRY(launch_small_gemm(gb, 2, s));
+    // layer 1 of both trunks
+    gb.job[0] = bwd_weight_job(states, idx, B, S, dh1p, H1, grads + L.off[P_W1], grads + L.off[P_B1]);
+    gb.job[1] = bwd_weight_job(states, idx, B, S, dh1v, H1, grads + L.off[P_V1], grads + L.off[P_VB1]);
+    return launch_small_gemm(gb, 2, s);
+}
+
+}  // namespace
+}  // namespace cpb
+
+using namespace cpb;
+
+extern "C" {
+
+int32_t cpb_ppo_num_tensors(void) { return P_COUNT; }
+const char* cpb_ppo_tensor_name(int32_t i) { return (i >= 0 && i < P_COUNT) ? kPpoNames[i] : nullptr; }
+
+int32_t cpb_ppo_layout(const cpb_ppo_config* cfg, int64_t* offsets, int64_t* sizes, int32_t* shapes, int64_t* total) {
+    CPB_TRY(check_ppo_cfg(cfg));
+    PpoLayout L = make_ppo_layout(cfg);
+    for (int i = 0; i < P_COUNT; ++i) {
+        if (offsets) offsets[i] = L.off[i];
+        if (sizes) sizes[i] = L.size[i];
+        if (shapes) { shapes[i * 2] = L.shape[i][0]; shapes[i * 2 + 1] = L.shape[i][1]; }
+    }
+    if (total) *total = L.total;
+    return CPB_OK;
+}
+
+int64_t cpb_ppo_workspace_bytes(const cpb_ppo_config* cfg, int32_t max_batch, int32_t horizon) {
+    if (check_ppo_cfg(cfg) != CPB_OK || max_batch < 1 || horizon < 0) return CPB_ERR_INVALID_ARGUMENT;
+    return make_ppo_plan(nullptr, 0, cfg, max_batch, horizon).bytes;
+}
+
+#define CPB_PPO_PLAN(maxb, horizon)                                                            \
+    CPB_TRY(check_ppo_cfg(cfg));                                                               \
+    CPB_REQUIRE(workspace != nullptr, "workspace is NULL");                                    \
+    PpoPlan pl = make_ppo_plan(workspace, workspace_bytes, cfg, maxb, horizon);                \
+    if (!pl.ok) {                                                                              \
+        cpb::set_error("ppo workspace too small: need %lld bytes, got %lld", (long long)pl.bytes, \
+                       (long long)workspace_bytes);                                            \
+        return CPB_ERR_WORKSPACE_TOO_SMALL;                                                    \
+    }                                                                                          \
+    PpoLayout L = make_ppo_layout(cfg);                                                        \
+    cudaStream_t s = (cudaStream_t)stream;
+
+int32_t cpb_ppo_forward(const cpb_ppo_config* cfg, const float* params, const float* states, int32_t batch,
+                        const float* noise, float* action, float* value, void* workspace, int64_t workspace_bytes,
+                        void* stream) {
+    CPB_REQUIRE(batch >= 1, "ppo_forward: batch must be >= 1");
+    CPB_PPO_PLAN(batch, 0);
+    CPB_REQUIRE(params && states && action && value, "ppo_forward: NULL pointer");
+    CPB_TRY(run_trunks(cfg, L, pl, params, states, nullptr, batch, s));
+    HeadArgs h = head_args(cfg, L, params, batch);
+    h.h2 = pl.h2; h.g2 = pl.h2 + (long long)batch * cfg->hidden2; h.noise = noise; h.action_out = action; h.v_out = value;
+    ppo_head_kernel<2><<<cdiv(batch, 8), 256, 0, s>>>(h);
+    CPB_LAUNCHED();
+    return CPB_OK;
+}
+
+int32_t cpb_ppo_loss_grad(const cpb_ppo_config* cfg, const float* params, const float* params_old,
+                          const float* states, const float* actions, const float* returns, const float* advantages,
+                          const int32_t* idx, int32_t batch, float* grads, float* metrics, void* workspace,
+                          int64_t workspace_bytes, void* stream) {
+    CPB_REQUIRE(batch >= 1, "ppo_loss_grad: batch must be >= 1");
+    CPB_PPO_PLAN(batch, 0);
+    CPB_REQUIRE(params && params_old && states && actions && returns && advantages && grads, "ppo_loss_grad: NULL pointer");
+    CPB_TRY(launch_fill_zero(grads, L.total, s));
+    CPB_TRY(run_old_logp(cfg, L, pl, params_old, states, actions, idx, batch, s));
+    return run_loss_grad(cfg, L, pl, params, states, actions, returns, advantages, idx, batch, pl.logp_old, 0, grads,
+                         metrics, s);
+}
+
+int32_t cpb_ppo_train_step(const cpb_ppo_config* cfg, float* params, const float* params_old, float* grads,
+                           float* adam_m, float* adam_v, float* adam_powers, const float* lr_dev, const float* states,
+                           const float* actions, const float* returns, const float* advantages, const int32_t* idx,
+                           int32_t batch, float* metrics, void* workspace, int64_t workspace_bytes, void* stream) {
+    CPB_REQUIRE(lr_dev != nullptr, "ppo_train_step: lr_dev is NULL");
+    CPB_TRY(cpb_ppo_loss_grad(cfg, params, params_old, states, actions, returns, advantages, idx, batch, grads, metrics,
+                              workspace, workspace_bytes, stream));
+    PpoLayout L = make_ppo_layout(cfg);
+    return launch_adam(params, grads, adam_m, adam_v, L.total, adam_powers, 0.f, lr_dev, 0.9f, 0.999f, 1e-8f,
+                       (cudaStream_t)stream);
+}
+
+int32_t cpb_gae(const double* rewards, const double* values, double bootstrap_value, const double* dones, int32_t T,
+                double gamma, double lam, double* advantages, double* returns, double* advantages_norm, void* stream) {
+    CPB_REQUIRE(rewards && values && dones && T >= 1, "gae: bad arguments");
+    CPB_REQUIRE(advantages != nullptr, "gae: advantages output is required");
+    gae_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(rewards, values, bootstrap_value, dones, T, gamma, lam, advantages,
+                                                      returns, advantages_norm, nullptr, nullptr, nullptr);
+    CPB_LAUNCHED();
+    return CPB_OK;
+}
+
+int32_t cpb_ppo_learn(const cpb_ppo_config* cfg, float* params, float* params_old, float* grads, float* adam_m,
+                      float* adam_v, float* adam_powers, const float* lr_dev, const float* states,
+                      const float* actions, const double* rewards, const double* values, double bootstrap_value,
+                      const double* dones, int32_t T, double gamma, double lam, int32_t num_epochs,
+                      int32_t batch_size, const int32_t* perms, float* metrics, void* workspace,
+                      int64_t workspace_bytes, void* stream) {
+    CPB_REQUIRE(T >= 1 && batch_size >= 1 && num_epochs >= 0, "ppo_learn: bad sizes");
+    CPB_PPO_PLAN(batch_size < T ? batch_size : T, T);
+    CPB_REQUIRE(params && params_old && grads && adam_m && adam_v && adam_powers && lr_dev && states && actions &&
+                rewards && values && dones && perms, "ppo_learn: NULL pointer");
+    // GAE, returns, normalised advantages (float64), rounded to float32 like the reference's feed
+    gae_kernel<<<1, 1024, 0, s>>>(rewards, values, bootstrap_value, dones, T, gamma, lam, nullptr, nullptr, nullptr,
+                                  pl.ret32, pl.adv32, pl.gae_scratch);
+    CPB_LAUNCHED();
+    // theta_old <- theta (PPO.update_old_policy, ppo.py:275-276)
+    CPB_CUDA(cudaMemcpyAsync(params_old, params, L.total * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    // log pi_old(a_t|s_t) is constant during the update: evaluate it once for all T samples
+    CPB_TRY(run_old_logp(cfg, L, pl, params_old, states, actions, nullptr, T, s));
+    CPB_TRY(launch_fill_zero(grads, L.total, s));
+    const int nmb = cdiv(T, batch_size);
+    for (int e = 0; e < num_epochs; ++e)
+        for (int i = 0; i < nmb; ++i) {
+            const int begin = i * batch_size;
+            const int B = begin + batch_size <= T ? batch_size : T - begin;
+            const int32_t* idx = perms + (long long)e * T + begin;
+            float* mt = metrics ? metrics + ((long long)e * nmb + i) * 5 : nullptr;
+            CPB_TRY(run_loss_grad(cfg, L, pl, params, states, actions, pl.ret32, pl.adv32, idx, B, pl.logp_old, 1,
+                                  grads, mt, s));
+            CPB_TRY(launch_adam(params, grads, adam_m, adam_v, L.total, adam_powers, 0.f, lr_dev, 0.9f, 0.999f, 1e-8f, s));
+        }
+    return CPB_OK;
+}
+
+}  // extern "C"

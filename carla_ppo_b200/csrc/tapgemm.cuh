@@ -1,0 +1,65 @@
+// Tap-GEMM: the one fp32 kernel family behind every dense contraction of the ConvVAE
+// (conv forward, transposed-conv forward, both data-gradients and the dense layers).
+//
+//   dst[pix(m), n] = epilogue( sum_{tap} sum_{c < C}  src[row(m) + tap.src_off + c] * W[tap.w_off + c*ldw + n] )
+//
+// A "tap" is one contiguous run of C source floats per output position plus the [C x N] weight
+// block that multiplies it:
+//   * gather form (tf Conv2D fwd, conv2d_transpose data-gradient): one tap per kernel row kh, the run
+//     is the (kw, cb) span of the stride-2 window -- always in bounds (VALID padding);
+//   * scatter form (conv2d_transpose fwd = Conv2DBackpropInput, Conv2D data-gradient): outputs are
+//     split into the 4 (y%2, x%2) parity classes; inside a class the layer is a stride-1 correlation
+//     with the taps {kh = py+2j, kw = px+2i}, bounds-checked (zero-filled) at the image border;
+//   * dense layers are 1x1 images with one tap (two for the fused heads' input gradient).
+#pragma once
+#include "common.cuh"
+
+namespace cpb {
+
+constexpr int kMaxTaps = 25;
+
+struct Tap {
+    int dy, dx;           // source pixel displacement (bounds check only)
+    long long src_off;    // float offset added to the row base
+    long long w_off;      // float offset of this tap's [C x N] weight block
+};
+
+struct TapClass {
+    int ntaps;
+    int py, px;           // destination parity offset (0 for gather form)
+    int Ho, Wo;           // output grid of this class
+    Tap taps[kMaxTaps];
+};
+
+struct TapGemmParams {
+    const float* src;
+    const float* wmat;
+    const float* bias;    // [N] or nullptr
+    const float* mask;    // same shape as dst: out *= (mask > 0), or nullptr
+    float* dst;
+    int batch;
+    int Hs, Ws;           // source image extent (pixels)
+    int src_pitch;        // floats per source pixel
+    long long src_img;    // floats per source image
+    int sstride;          // source pixels per output step (2 gather, 1 scatter/dense)
+    int C;                // floats per tap run (multiple of 16)
+    int N;                // output channels handled per y-batch (multiple of the tile's BN)
+    int ldw;              // weight row stride in floats
+    int Hd, Wd;           // destination image extent
+    int dstride;          // destination pixels per output step (1 gather, 2 scatter)
+    int dst_pitch;        // floats per destination pixel
+    long long dst_img;    // floats per destination image
+    int relu;
+    int check;            // bounds-check taps (scatter form)
+    int nclass;           // 1 or 4
+    int ybatch;           // independent problems sharing src (fused heads): 1 or 2
+    long long w_ystride, bias_ystride, dst_ystride;
+    TapClass cls[4];
+};
+
+// Enqueue; picks the tile shape from N and the row count.
+int32_t launch_tapgemm(const TapGemmParams& p, cudaStream_t stream);
+// One-time opt-in for >48 KB dynamic shared memory (called from the API layer).
+int32_t tapgemm_init();
+
+}  // namespace cpb

@@ -1,0 +1,652 @@
+// ConvVAE orchestration behind the C ABI (include/carla_ppo_b200.h).
+// Replaces the TF graph built by reference vae/models.py:85-142 + 249-266 and the sess.run calls of
+// VAE.encode / generate_from_latent / reconstruct / evaluate / train_one_epoch (:188-231).
+#include <mutex>
+#include <stdarg.h>
+
+#include "elementwise.cuh"
+#include "tapgemm.cuh"
+#include "wgrad.cuh"
+
+namespace cpb {
+
+static thread_local char g_err[512] = "";
+int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static std::once_flag g_init_once;
+static int32_t g_init_status = CPB_OK;
+int32_t ensure_init() {
+    std::call_once(g_init_once, [] {
+        g_init_status = tapgemm_init();
+        if (g_init_status == CPB_OK) g_init_status = wgrad_init();
+    });
+    return g_init_status;
+}
+
+// ---------------------------------------------------------------------------------------------
+// geometry (source 80x160x3, reference vae_common.py:18-20; layer table SURVEY appendix A.1)
+// ---------------------------------------------------------------------------------------------
+namespace geo {
+constexpr int H0 = 80, W0 = 160;
+constexpr int H1 = 39, W1 = 79, C1 = 32;
+constexpr int H2 = 18, W2 = 38, C2 = 64;
+constexpr int H3 = 8, W3 = 18, C3 = 128;
+constexpr int H4 = 3, W4 = 8, C4 = 256;
+constexpr int FEAT = H4 * W4 * C4;   // 6144
+constexpr int NPIX = H0 * W0;        // 12800
+}  // namespace geo
+
+enum VaeTensor {
+    T_CONV1_K, T_CONV1_B, T_CONV2_K, T_CONV2_B, T_CONV3_K, T_CONV3_B, T_CONV4_K, T_CONV4_B,
+    T_MEAN_K, T_MEAN_B, T_LOGVAR_K, T_LOGVAR_B, T_DENSE1_K, T_DENSE1_B,
+    T_DECONV1_K, T_DECONV1_B, T_DECONV2_K, T_DECONV2_B, T_DECONV3_K, T_DECONV3_B, T_DECONV4_K, T_DECONV4_B,
+    T_COUNT
+};
+
+static const char* kVaeNames[T_COUNT] = {
+    "encoder/conv1/kernel", "encoder/conv1/bias", "encoder/conv2/kernel", "encoder/conv2/bias",
+    "encoder/conv3/kernel", "encoder/conv3/bias", "encoder/conv4/kernel", "encoder/conv4/bias",
+    "mean/kernel", "mean/bias", "logstd_sqare/kernel", "logstd_sqare/bias",
+    "decoder/dense1/kernel", "decoder/dense1/bias",
+    "decoder/deconv1/kernel", "decoder/deconv1/bias", "decoder/deconv2/kernel", "decoder/deconv2/bias",
+    "decoder/deconv3/kernel", "decoder/deconv3/bias", "decoder/deconv4/kernel", "decoder/deconv4/bias"};
+
+struct VaeLayout {
+    int64_t off[T_COUNT];
+    int64_t size[T_COUNT];
+    int32_t shape[T_COUNT][4];
+    int64_t total;
+};
+
+static void set_shape(VaeLayout& L, int t, int a, int b = 0, int c = 0, int d = 0) {
+    L.shape[t][0] = a; L.shape[t][1] = b; L.shape[t][2] = c; L.shape[t][3] = d;
+    int64_t n = a;
+    if (b) n *= b;
+    if (c) n *= c;
+    if (d) n *= d;
+    L.size[t] = n;
+}
+
+static VaeLayout make_layout(int ct, int z) {
+    using namespace geo;
+    VaeLayout L;
+    set_shape(L, T_CONV1_K, 4, 4, 3, C1);    set_shape(L, T_CONV1_B, C1);
+    set_shape(L, T_CONV2_K, 4, 4, C1, C2);   set_shape(L, T_CONV2_B, C2);
+    set_shape(L, T_CONV3_K, 4, 4, C2, C3);   set_shape(L, T_CONV3_B, C3);
+    set_shape(L, T_CONV4_K, 4, 4, C3, C4);   set_shape(L, T_CONV4_B, C4);
+    set_shape(L, T_MEAN_K, FEAT, z);         set_shape(L, T_MEAN_B, z);
+    set_shape(L, T_LOGVAR_K, FEAT, z);       set_shape(L, T_LOGVAR_B, z);
+    set_shape(L, T_DENSE1_K, z, FEAT);       set_shape(L, T_DENSE1_B, FEAT);
+    set_shape(L, T_DECONV1_K, 4, 4, C3, C4); set_shape(L, T_DECONV1_B, C3);
+    set_shape(L, T_DECONV2_K, 4, 4, C2, C3); set_shape(L, T_DECONV2_B, C2);
+    set_shape(L, T_DECONV3_K, 5, 5, C1, C2); set_shape(L, T_DECONV3_B, C1);
+    set_shape(L, T_DECONV4_K, 4, 4, ct, C1); set_shape(L, T_DECONV4_B, ct);
+    // storage order: TF creation order, except that the two head kernels (and the two head biases) are
+    // adjacent so that both heads run as one y-batched tap-GEMM.
+    static const int order[T_COUNT] = {
+        T_CONV1_K, T_CONV1_B, T_CONV2_K, T_CONV2_B, T_CONV3_K, T_CONV3_B, T_CONV4_K, T_CONV4_B,
+        T_MEAN_K, T_LOGVAR_K, T_MEAN_B, T_LOGVAR_B, T_DENSE1_K, T_DENSE1_B,
+        T_DECONV1_K, T_DECONV1_B, T_DECONV2_K, T_DECONV2_B, T_DECONV3_K, T_DECONV3_B, T_DECONV4_K, T_DECONV4_B};
+    int64_t o = 0;
+    for (int i = 0; i < T_COUNT; ++i) {
+        L.off[order[i]] = o;
+        o += align_up(L.size[order[i]], 64);
+    }
+    L.total = o;
+    return L;
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace plan
+// ---------------------------------------------------------------------------------------------
+struct Relayout {
+    int64_t conv2T, conv3T, conv4T, deconv1T, deconv2T, deconv3T, dense1T, headsT, conv1P, deconv4P;
+    int64_t total;
+};
+
+static Relayout make_relayout(int z) {
+    using namespace geo;
+    Relayout r;
+    int64_t o = 0;
+    auto take = [&](int64_t n) { int64_t at = o; o += align_up(n, 64); return at; };
+    r.conv2T = take(16LL * C1 * C2);
+    r.conv3T = take(16LL * C2 * C3);
+    r.conv4T = take(16LL * C3 * C4);
+    r.deconv1T = take(16LL * C3 * C4);
+    r.deconv2T = take(16LL * C2 * C3);
+    r.deconv3T = take(25LL * C1 * C2);
+    r.dense1T = take((int64_t)z * FEAT);
+    r.headsT = take(2LL * z * FEAT);
+    r.conv1P = take(16LL * 4 * C1);
+    r.deconv4P = take(16LL * 4 * C1);
+    r.total = o;
+    return r;
+}
+
+struct VaePlan {
+    int B, ct, z, mode;
+    Relayout rl;
+    float *relayout, *xp, *yp, *a1, *a2, *a3, *a4, *heads, *zbuf, *kl_rows, *kl_active, *frame_loss;
+    float *d1, *b1, *b2, *b3, *logits_p;
+    float *gA, *gB, *gz, *gheads, *partial, *colsum;
+    int64_t bytes;
+    bool ok;
+};
+
+static int64_t max_partial_floats(int B, int z) {
+    using namespace geo;
+    struct P { int I, J; long long M; };
+    const P ps[] = {
+        {64, C1, (long long)B * H1 * W1},          // conv1 / deconv4 (padded to 4 channels)
+        {16 * C1, C2, (long long)B * H2 * W2},     // conv2
+        {16 * C2, C3, (long long)B * H3 * W3},     // conv3 / deconv2
+        {16 * C3, C4, (long long)B * H4 * W4},     // conv4 / deconv1
+        {25 * C1, C2, (long long)B * H2 * W2},     // deconv3
+        {FEAT, z, (long long)B},                    // heads
+        {z, FEAT, (long long)B},                    // dense1
+    };
+    int64_t best = 0;
+    for (const P& p : ps) {
+        int64_t n = (int64_t)wgrad_pick_splits(p.I, p.J, p.M) * p.I * p.J;
+        if (n > best) best = n;
+    }
+    return best;
+}
+
+static VaePlan make_plan(void* ws, int64_t ws_bytes, int B, int ct, int z, int mode) {
+    using namespace geo;
+    VaePlan p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.ct = ct; p.z = z; p.mode = mode;
+    p.rl = make_relayout(z);
+    Arena a(ws, ws_bytes);
+    const int64_t b = B;
+    p.relayout = a.take<float>(p.rl.total);
+    p.xp = a.take<float>(b * NPIX * 4);
+    p.a1 = a.take<float>(b * H1 * W1 * C1);
+    p.a2 = a.take<float>(b * H2 * W2 * C2);
+    p.a3 = a.take<float>(b * H3 * W3 * C3);
+    p.a4 = a.take<float>(b * FEAT);
+    p.heads = a.take<float>(2 * b * z);
+    if (mode >= CPB_WS_FORWARD) {
+        p.yp = a.take<float>(b * NPIX * 4);
+        p.zbuf = a.take<float>(b * z);
+        p.kl_rows = a.take<float>(b);
+        p.kl_active = a.take<float>(b);
+        p.frame_loss = a.take<float>(b);
+        p.d1 = a.take<float>(b * FEAT);
+        p.b1 = a.take<float>(b * H3 * W3 * C3);
+        p.b2 = a.take<float>(b * H2 * W2 * C2);
+        p.b3 = a.take<float>(b * H1 * W1 * C1);
+        p.logits_p = a.take<float>(b * NPIX * 4);
+    }
+    if (mode >= CPB_WS_TRAIN) {
+        p.gA = a.take<float>(b * H1 * W1 * C1);
+        p.gB = a.take<float>(b * H1 * W1 * C1);
+        p.gz = a.take<float>(b * z);
+        p.gheads = a.take<float>(2 * b * z);
+        p.partial = a.take<float>(max_partial_floats(B, z));
+        p.colsum = a.take<float>(colsum_scratch_floats(b * NPIX, 4) + colsum_scratch_floats(b * H1 * W1, C1) +
+                                 colsum_scratch_floats(b, FEAT));
+    }
+    p.bytes = a.off;
+    p.ok = ws == nullptr || !a.overflow;
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tap-GEMM problem builders
+// ---------------------------------------------------------------------------------------------
+static TapGemmParams base_params() {
+    TapGemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.nclass = 1;
+    p.ybatch = 1;
+    return p;
+}
+
+// gather form: small[b,i,j,:] = sum_{kh,kw,cb} big[b,2i+kh,2j+kw,cb] * W[kh,kw,cb,:]
+static TapGemmParams gather_problem(const float* big, int B, int Hb, int Wb, int pitch, int k, const float* W,
+                                    int N, const float* bias, const float* mask, float* small, int relu) {
+    TapGemmParams p = base_params();
+    p.src = big; p.wmat = W; p.bias = bias; p.mask = mask; p.dst = small;
+    p.batch = B; p.Hs = Hb; p.Ws = Wb; p.src_pitch = pitch; p.src_img = (long long)Hb * Wb * pitch;
+    p.sstride = 2; p.C = k * pitch; p.N = N; p.ldw = N;
+    const int Ho = (Hb - k) / 2 + 1, Wo = (Wb - k) / 2 + 1;
+    p.Hd = Ho; p.Wd = Wo; p.dstride = 1; p.dst_pitch = N; p.dst_img = (long long)Ho * Wo * N;
+    p.relu = relu; p.check = 0;
+    TapClass& c = p.cls[0];
+    c.ntaps = k; c.py = c.px = 0; c.Ho = Ho; c.Wo = Wo;
+    for (int kh = 0; kh < k; ++kh) {
+        c.taps[kh].dy = kh; c.taps[kh].dx = 0;
+        c.taps[kh].src_off = (long long)kh * Wb * pitch;
+        c.taps[kh].w_off = (long long)kh * k * pitch * N;
+    }
+    return p;
+}
+
+// scatter form: big[b,2i+kh,2j+kw,cb] += small[b,i,j,cs] * W[kh,kw,cb,cs]; Wt is [kh][kw][cs][cb]
+static TapGemmParams scatter_problem(const float* small, int B, int Hs, int Ws, int Cs, int k, const float* Wt,
+                                     int Cb, const float* bias, const float* mask, float* big, int Hb, int Wb,
+                                     int relu) {
+    TapGemmParams p = base_params();
+    p.src = small; p.wmat = Wt; p.bias = bias; p.mask = mask; p.dst = big;
+    p.batch = B; p.Hs = Hs; p.Ws = Ws; p.src_pitch = Cs; p.src_img = (long long)Hs * Ws * Cs;
+    p.sstride = 1; p.C = Cs; p.N = Cb; p.ldw = Cb;
+    p.Hd = Hb; p.Wd = Wb; p.dstride = 2; p.dst_pitch = Cb; p.dst_img = (long long)Hb * Wb * Cb;
+    p.relu = relu; p.check = 1; p.nclass = 4;
+    for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+            TapClass& c = p.cls[py * 2 + px];
+            c.py = py; c.px = px;
+            c.Ho = (Hb - py + 1) / 2; c.Wo = (Wb - px + 1) / 2;
+            int n = 0;
+            for (int kh = py, j = 0; kh < k; kh += 2, ++j)
+                for (int kw = px, i = 0; kw < k; kw += 2, ++i) {
+                    Tap& t = c.taps[n++];
+                    t.dy = -j; t.dx = -i;
+                    t.src_off = ((long long)(-j) * Ws - i) * Cs;
+                    t.w_off = ((long long)kh * k + kw) * Cs * Cb;
+                }
+            c.ntaps = n;
+        }
+    return p;
+}
+
+// dense: dst[b, :N] = src[b, :K] @ W[K, ldw] (+bias)
+static TapGemmParams dense_problem(const float* src, int B, int K, const float* W, int N, const float* bias,
+                                   const float* mask, float* dst, int relu) {
+    TapGemmParams p = base_params();
+    p.src = src; p.wmat = W; p.bias = bias; p.mask = mask; p.dst = dst;
+    p.batch = B; p.Hs = p.Ws = 1; p.src_pitch = K; p.src_img = K; p.sstride = 1; p.C = K; p.N = N; p.ldw = N;
+    p.Hd = p.Wd = 1; p.dstride = 1; p.dst_pitch = N; p.dst_img = N; p.relu = relu; p.check = 0;
+    TapClass& c = p.cls[0];
+    c.ntaps = 1; c.py = c.px = 0; c.Ho = c.Wo = 1;
+    c.taps[0].dy = c.taps[0].dx = 0; c.taps[0].src_off = 0; c.taps[0].w_off = 0;
+    return p;
+}
+
+static int32_t run_wgrad(const float* big, int Wb, int pitch, long long big_img, int k, const float* small, int B,
+                         int Ho, int Wo, int J, int c_pad, int c_real, float* partial, float* out, cudaStream_t s) {
+    WgradParams w;
+    memset(&w, 0, sizeof(w));
+    w.big = big; w.small = small; w.partial = partial;
+    w.batch = B; w.Wb = Wb; w.big_pitch = pitch; w.big_img = big_img; w.Ho = Ho; w.Wo = Wo; w.sstride = 2;
+    w.ntaps = k; w.run = k * pitch;
+    for (int kh = 0; kh < k; ++kh) w.tap_off[kh] = (long long)kh * Wb * pitch;
+    w.I = k * k * pitch; w.J = J;
+    const long long M = (long long)B * Ho * Wo;
+    w.splits = wgrad_pick_splits(w.I, w.J, M);
+    w.m_per_split = align_up((M + w.splits - 1) / w.splits, 16);
+    CPB_TRY(launch_wgrad(w, s));
+    return launch_reduce_partials(partial, w.splits, w.I, w.J, c_pad, c_real, out, s);
+}
+
+static int32_t run_dense_wgrad(const float* x, int K, const float* g, int B, int J, float* partial, float* out,
+                               cudaStream_t s) {
+    WgradParams w;
+    memset(&w, 0, sizeof(w));
+    w.big = x; w.small = g; w.partial = partial;
+    w.batch = B; w.Wb = 1; w.big_pitch = K; w.big_img = K; w.Ho = w.Wo = 1; w.sstride = 1;
+    w.ntaps = 1; w.run = K; w.tap_off[0] = 0; w.I = K; w.J = J;
+    w.splits = wgrad_pick_splits(w.I, w.J, B);
+    w.m_per_split = align_up(((long long)B + w.splits - 1) / w.splits, 16);
+    CPB_TRY(launch_wgrad(w, s));
+    return launch_reduce_partials(partial, w.splits, w.I, w.J, K, K, out, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// passes
+// ---------------------------------------------------------------------------------------------
+static int32_t check_cfg(const cpb_vae_config* cfg) {
+    CPB_REQUIRE(cfg != nullptr, "cfg is NULL");
+    CPB_REQUIRE(cfg->batch >= 1 && cfg->batch <= (1 << 20), "batch=%d out of range", cfg->batch);
+    CPB_REQUIRE(cfg->target_channels == 1 || cfg->target_channels == 3, "target_channels must be 1 or 3, got %d", cfg->target_channels);
+    CPB_REQUIRE(cfg->z_dim >= 64 && cfg->z_dim % 64 == 0 && cfg->z_dim <= 1024, "z_dim=%d must be a multiple of 64 in [64,1024]", cfg->z_dim);
+    CPB_REQUIRE(cfg->loss_type >= 0 && cfg->loss_type <= 2, "unknown loss_type %d", cfg->loss_type);
+    CPB_REQUIRE(cfg->source_dtype == CPB_FRAME_F32 || cfg->source_dtype == CPB_FRAME_U8, "bad source_dtype");
+    CPB_REQUIRE(cfg->target_dtype == CPB_FRAME_F32 || cfg->target_dtype == CPB_FRAME_U8, "bad target_dtype");
+    return CPB_OK;
+}
+
+static int32_t relayout_weights(const VaePlan& pl, const VaeLayout& L, const float* params, bool decoder,
+                                bool backward, cudaStream_t s) {
+    using namespace geo;
+    RelayoutTable t;
+    memset(&t, 0, sizeof(t));
+    auto add = [&](int64_t src, int64_t dst, int taps, int rows, int cols, int mode, int rows_pad) {
+        RelayoutJob& j = t.jobs[t.njobs++];
+        j.src_off = src; j.dst_off = dst; j.taps = taps; j.rows = rows; j.cols = cols; j.mode = mode;
+        j.rows_pad = rows_pad;
+        j.count = mode == 0 ? (long long)taps * rows * cols : (long long)taps * rows_pad * cols;
+        t.total += j.count;
+    };
+    add(L.off[T_CONV1_K], pl.rl.conv1P, 16, 3, C1, 1, 4);
+    if (decoder) {
+        add(L.off[T_DECONV1_K], pl.rl.deconv1T, 16, C3, C4, 0, 0);
+        add(L.off[T_DECONV2_K], pl.rl.deconv2T, 16, C2, C3, 0, 0);
+        add(L.off[T_DECONV3_K], pl.rl.deconv3T, 25, C1, C2, 0, 0);
+    }
+    if (backward) {
+        add(L.off[T_CONV2_K], pl.rl.conv2T, 16, C1, C2, 0, 0);
+        add(L.off[T_CONV3_K], pl.rl.conv3T, 16, C2, C3, 0, 0);
+        add(L.off[T_CONV4_K], pl.rl.conv4T, 16, C3, C4, 0, 0);
+        add(L.off[T_DENSE1_K], pl.rl.dense1T, 1, pl.z, FEAT, 0, 0);
+        add(L.off[T_MEAN_K], pl.rl.headsT, 2, FEAT, pl.z, 0, 0);   // mean and logvar kernels are adjacent
+        add(L.off[T_DECONV4_K], pl.rl.deconv4P, 16, pl.ct, C1, 1, 4);
+    }
+    return launch_relayout(params, pl.relayout, t, s);
+}
+
+static int32_t run_encoder(const VaePlan& pl, const VaeLayout& L, const cpb_vae_config* cfg, const float* params,
+                           const void* source, int32_t* flags, cudaStream_t s) {
+    using namespace geo;
+    const int B = pl.B;
+    const float sscale = cfg->source_dtype == CPB_FRAME_U8 ? 1.f / 255.f : 1.f;
+    CPB_TRY(launch_prep_frames(source, cfg->source_dtype, sscale, 3, (long long)B * NPIX, pl.xp, flags, 1, s));
+    TapGemmParams p = gather_problem(pl.xp, B, H0, W0, 4, 4, pl.relayout + pl.rl.conv1P, C1,
+                                     params + L.off[T_CONV1_B], nullptr, pl.a1, 1);
+    CPB_TRY(launch_tapgemm(p, s));
+    p = gather_problem(pl.a1, B, H1, W1, C1, 4, params + L.off[T_CONV2_K], C2, params + L.off[T_CONV2_B], nullptr, pl.a2, 1);
+    CPB_TRY(launch_tapgemm(p, s));
+    p = gather_problem(pl.a2, B, H2, W2, C2, 4, params + L.off[T_CONV3_K], C3, params + L.off[T_CONV3_B], nullptr, pl.a3, 1);
+    CPB_TRY(launch_tapgemm(p, s));
+    p = gather_problem(pl.a3, B, H3, W3, C3, 4, params + L.off[T_CONV4_K], C4, params + L.off[T_CONV4_B], nullptr, pl.a4, 1);
+    CPB_TRY(launch_tapgemm(p, s));
+    // both heads as one y-batched dense problem: heads[0] = mean, heads[1] = logstd_sq
+    p = dense_problem(pl.a4, B, FEAT, params + L.off[T_MEAN_K], pl.z, params + L.off[T_MEAN_B], nullptr, pl.heads, 0);
+    p.ybatch = 2;
+    p.w_ystride = L.off[T_LOGVAR_K] - L.off[T_MEAN_K];
+    p.bias_ystride = L.off[T_LOGVAR_B] - L.off[T_MEAN_B];
+    p.dst_ystride = (long long)B * pl.z;
+    return launch_tapgemm(p, s);
+}
+
+// zbuf -> d1 -> b1 -> b2 -> b3 -> (logits_p and/or sigmoid)
+static int32_t run_decoder(const VaePlan& pl, const VaeLayout& L, const float* params, const float* zsrc,
+                           float* logits_p, float* sigm, cudaStream_t s) {
+    using namespace geo;
+    const int B = pl.B;
+    TapGemmParams p = dense_problem(zsrc, B, pl.z, params + L.off[T_DENSE1_K], FEAT, params + L.off[T_DENSE1_B],
+                                    nullptr, pl.d1, 0);
+    CPB_TRY(launch_tapgemm(p, s));
+    p = scatter_problem(pl.d1, B, H4, W4, C4, 4, pl.relayout + pl.rl.deconv1T, C3, params + L.off[T_DECONV1_B],
+                        nullptr, pl.b1, H3, W3, 1);
+    CPB_TRY(launch_tapgemm(p, s));
+    p = scatter_problem(pl.b1, B, H3, W3, C3, 4, pl.relayout + pl.rl.deconv2T, C2, params + L.off[T_DECONV2_B],
+                        nullptr, pl.b2, H2, W2, 1);
+    CPB_TRY(launch_tapgemm(p, s));
+    p = scatter_problem(pl.b2, B, H2, W2, C2, 5, pl.relayout + pl.rl.deconv3T, C1, params + L.off[T_DECONV3_B],
+                        nullptr, pl.b3, H1, W1, 1);
+    CPB_TRY(launch_tapgemm(p, s));
+    return launch_deconv4_fwd(pl.b3, params + L.off[T_DECONV4_K], params + L.off[T_DECONV4_B], B, pl.ct, logits_p,
+                              sigm, s);
+}
+
+static int32_t run_forward_loss(const VaePlan& pl, const VaeLayout& L, const cpb_vae_config* cfg, const float* params,
+                                const void* source, const void* target, const float* eps, bool want_dlogits,
+                                float* sigm, int32_t* flags, cudaStream_t s) {
+    using namespace geo;
+    const int B = pl.B;
+    CPB_TRY(run_encoder(pl, L, cfg, params, source, flags, s));
+    CPB_TRY(launch_reparam(pl.heads, eps, B, pl.z, cfg->kl_tolerance, pl.zbuf, pl.kl_rows, pl.kl_active, s));
+    CPB_TRY(run_decoder(pl, L, params, pl.zbuf, pl.logits_p, sigm, s));
+    const float* yp = pl.yp;
+    if (target == source && cfg->target_channels == 3 && cfg->target_dtype == cfg->source_dtype &&
+        (cfg->target_dtype == CPB_FRAME_F32 || cfg->target_u8_scale == 1.f / 255.f)) {
+        yp = pl.xp;   // rgb target == source (vae/train_vae.py:75): already prepared and range-checked
+    } else {
+        const float tscale = cfg->target_dtype == CPB_FRAME_U8 ? cfg->target_u8_scale : 1.f;
+        CPB_TRY(launch_prep_frames(target, cfg->target_dtype, tscale, cfg->target_channels, (long long)B * NPIX,
+                                   pl.yp, flags, 2, s));
+    }
+    const float gscale = cfg->loss_scale / (float)B;
+    CPB_TRY(launch_recon_loss(pl.logits_p, yp, B, pl.ct, cfg->loss_type, gscale, pl.frame_loss,
+                              want_dlogits ? pl.logits_p : nullptr, s));
+    return CPB_OK;
+}
+
+static int32_t run_backward(const VaePlan& pl, const VaeLayout& L, const cpb_vae_config* cfg, const float* params,
+                            const float* eps, float* grads, cudaStream_t s) {
+    using namespace geo;
+    const int B = pl.B;
+    const int z = pl.z;
+    float* dlog = pl.logits_p;   // overwritten in place by the loss kernel
+    float* cs = pl.colsum;
+    CPB_TRY(launch_fill_zero(grads, L.total, s));
+    // ---- deconv4 (padded to 4 channels on the big side)
+    CPB_TRY(run_wgrad(dlog, W0, 4, (long long)NPIX * 4, 4, pl.b3, B, H1, W1, C1, 4, pl.ct, pl.partial,
+                      grads + L.off[T_DECONV4_K], s));
+    CPB_TRY(launch_colsum(dlog, (long long)B * NPIX, 4, pl.ct, grads + L.off[T_DECONV4_B], cs, s));
+    TapGemmParams p = gather_problem(dlog, B, H0, W0, 4, 4, pl.relayout + pl.rl.deconv4P, C1, nullptr, pl.b3, pl.gA, 0);
+    CPB_TRY(launch_tapgemm(p, s));                                   // gA = g(b3 pre-activation)
+    // ---- deconv3
+    CPB_TRY(run_wgrad(pl.gA, W1, C1, (long long)H1 * W1 * C1, 5, pl.b2, B, H2, W2, C2, 5 * 5 * C1, 5 * 5 * C1,
+                      pl.partial, grads + L.off[T_DECONV3_K], s));
+    CPB_TRY(launch_colsum(pl.gA, (long long)B * H1 * W1, C1, C1, grads + L.off[T_DECONV3_B], cs, s));
+    p = gather_problem(pl.gA, B, H1, W1, C1, 5, params + L.off[T_DECONV3_K], C2, nullptr, pl.b2, pl.gB, 0);
+    CPB_TRY(launch_tapgemm(p, s));                                   // gB = g(b2)
+    // ---- deconv2
+    CPB_TRY(run_wgrad(pl.gB, W2, C2, (long long)H2 * W2 * C2, 4, pl.b1, B, H3, W3, C3, 16 * C2, 16 * C2, pl.partial,
+                      grads + L.off[T_DECONV2_K], s));
+    CPB_TRY(launch_colsum(pl.gB, (long long)B * H2 * W2, C2, C2, grads + L.off[T_DECONV2_B], cs, s));
+    p = gather_problem(pl.gB, B, H2, W2, C2, 4, params + L.off[T_DECONV2_K], C3, nullptr, pl.b1, pl.gA, 0);
+    CPB_TRY(launch_tapgemm(p, s));                                   // gA = g(b1)
+    // ---- deconv1
+    CPB_TRY(run_wgrad(pl.gA, W3, C3, (long long)H3 * W3 * C3, 4, pl.d1, B, H4, W4, C4, 16 * C3, 16 * C3, pl.partial,
+                      grads + L.off[T_DECONV1_K], s));
+    CPB_TRY(launch_colsum(pl.gA, (long long)B * H3 * W3, C3, C3, grads + L.off[T_DECONV1_B], cs, s));
+    p = gather_problem(pl.gA, B, H3, W3, C3, 4, params + L.off[T_DECONV1_K], C4, nullptr, nullptr, pl.gB, 0);
+    CPB_TRY(launch_tapgemm(p, s));                                   // gB = g(d1) [B, 6144]
+    // ---- dense1
+    CPB_TRY(run_dense_wgrad(pl.zbuf, z, pl.gB, B, FEAT, pl.partial, grads + L.off[T_DENSE1_K], s));
+    CPB_TRY(launch_colsum(pl.gB, B, FEAT, FEAT, grads + L.off[T_DENSE1_B], cs, s));
+    p = dense_problem(pl.gB, B, FEAT, pl.relayout + pl.rl.dense1T, z, nullptr, nullptr, pl.gz, 0);
+    CPB_TRY(launch_tapgemm(p, s));
+    // ---- sampling + KL
+    CPB_TRY(launch_reparam_bwd(pl.heads, eps, pl.gz, pl.kl_active, B, z, cfg->beta * cfg->loss_scale / (float)B,
+                               pl.gheads, s));
+    // ---- heads
+    CPB_TRY(run_dense_wgrad(pl.a4, FEAT, pl.gheads, B, z, pl.partial, grads + L.off[T_MEAN_K], s));
+    CPB_TRY(run_dense_wgrad(pl.a4, FEAT, pl.gheads + (long long)B * z, B, z, pl.partial, grads + L.off[T_LOGVAR_K], s));
+    CPB_TRY(launch_colsum(pl.gheads, B, z, z, grads + L.off[T_MEAN_B], cs, s));
+    CPB_TRY(launch_colsum(pl.gheads + (long long)B * z, B, z, z, grads + L.off[T_LOGVAR_B], cs, s));
+    p = dense_problem(pl.gheads, B, z, pl.relayout + pl.rl.headsT, FEAT, nullptr, pl.a4, pl.gA, 0);
+    p.cls[0].ntaps = 2;                                              // g(a4) = gmean Wm^T + glogvar Wl^T
+    p.cls[0].taps[1].dy = p.cls[0].taps[1].dx = 0;
+    p.cls[0].taps[1].src_off = (long long)B * z;
+    p.cls[0].taps[1].w_off = (long long)z * FEAT;
+    CPB_TRY(launch_tapgemm(p, s));                                   // gA = g(a4 pre-activation)
+    // ---- conv4
+    CPB_TRY(run_wgrad(pl.a3, W3, C3, (long long)H3 * W3 * C3, 4, pl.gA, B, H4, W4, C4, 16 * C3, 16 * C3, pl.partial,
+                      grads + L.off[T_CONV4_K], s));
+    CPB_TRY(launch_colsum(pl.gA, (long long)B * H4 * W4, C4, C4, grads + L.off[T_CONV4_B], cs, s));
+    p = scatter_problem(pl.gA, B, H4, W4, C4, 4, pl.relayout + pl.rl.conv4T, C3, nullptr, pl.a3, pl.gB, H3, W3, 0);
+    CPB_TRY(launch_tapgemm(p, s));                                   // gB = g(a3)
+    // ---- conv3
+    CPB_TRY(run_wgrad(pl.a2, W2, C2, (long long)H2 * W2 * C2, 4, pl.gB, B, H3, W3, C3, 16 * C2, 16 * C2, pl.partial,
+                      grads + L.off[T_CONV3_K], s));
+    CPB_TRY(launch_colsum(pl.gB, (long long)B * H3 * W3, C3, C3, grads + L.off[T_CONV3_B], cs, s));
+    p = scatter_problem(pl.gB, B, H3, W3, C3, 4, pl.relayout + pl.rl.conv3T, C2, nullptr, pl.a2, pl.gA, H2, W2, 0);
+    CPB_TRY(launch_tapgemm(p, s));                                   // gA = g(a2)
+    // ---- conv2
+    CPB_TRY(run_wgrad(pl.a1, W1, C1, (long long)H1 * W1 * C1, 4, pl.gA, B, H2, W2, C2, 16 * C1, 16 * C1, pl.partial,
+                      grads + L.off[T_CONV2_K], s));
+    CPB_TRY(launch_colsum(pl.gA, (long long)B * H2 * W2, C2, C2, grads + L.off[T_CONV2_B], cs, s));
+    p = scatter_problem(pl.gA, B, H2, W2, C2, 4, pl.relayout + pl.rl.conv2T, C1, nullptr, pl.a1, pl.gB, H1, W1, 0);
+    CPB_TRY(launch_tapgemm(p, s));                                   // gB = g(a1)
+    // ---- conv1 (its input gradient is never used: the reference computes and discards it)
+    CPB_TRY(run_wgrad(pl.xp, W0, 4, (long long)NPIX * 4, 4, pl.gB, B, H1, W1, C1, 4, 3, pl.partial,
+                      grads + L.off[T_CONV1_K], s));
+    CPB_TRY(launch_colsum(pl.gB, (long long)B * H1 * W1, C1, C1, grads + L.off[T_CONV1_B], cs, s));
+    return CPB_OK;
+}
+
+}  // namespace cpb
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace cpb;
+
+extern "C" {
+
+const char* cpb_last_error(void) { return cpb::g_err; }
+const char* cpb_build_info(void) { return "carla_ppo_b200 0.1 (sm_100a, fp32 SIMT tap-GEMM)"; }
+int64_t cpb_launch_count(void) { return cpb::g_launches; }
+void cpb_reset_launch_count(void) { cpb::g_launches = 0; }
+
+int32_t cpb_vae_num_tensors(void) { return T_COUNT; }
+const char* cpb_vae_tensor_name(int32_t i) { return (i >= 0 && i < T_COUNT) ? kVaeNames[i] : nullptr; }
+
+int32_t cpb_vae_layout(int32_t ct, int32_t z, int64_t* offsets, int64_t* sizes, int32_t* shapes, int64_t* total) {
+    CPB_REQUIRE(ct == 1 || ct == 3, "target_channels must be 1 or 3, got %d", ct);
+    CPB_REQUIRE(z >= 64 && z % 64 == 0 && z <= 1024, "z_dim=%d must be a multiple of 64 in [64,1024]", z);
+    VaeLayout L = make_layout(ct, z);
+    for (int i = 0; i < T_COUNT; ++i) {
+        if (offsets) offsets[i] = L.off[i];
+        if (sizes) sizes[i] = L.size[i];
+        if (shapes) for (int d = 0; d < 4; ++d) shapes[i * 4 + d] = L.shape[i][d];
+    }
+    if (total) *total = L.total;
+    return CPB_OK;
+}
+
+int64_t cpb_vae_workspace_bytes(int32_t batch, int32_t ct, int32_t z, int32_t mode) {
+    if (batch < 1 || (ct != 1 && ct != 3) || z < 64 || z % 64 != 0 || mode < 0 || mode > 2) {
+        cpb::set_error("cpb_vae_workspace_bytes: bad arguments");
+        return CPB_ERR_INVALID_ARGUMENT;
+    }
+    return make_plan(nullptr, 0, batch, ct, z, mode).bytes;
+}
+
+#define CPB_PLAN(mode)                                                                              \
+    CPB_TRY(check_cfg(cfg));                                                                        \
+    CPB_TRY(ensure_init());                                                                         \
+    CPB_REQUIRE(workspace != nullptr, "workspace is NULL");                                         \
+    VaePlan pl = make_plan(workspace, workspace_bytes, cfg->batch, cfg->target_channels, cfg->z_dim, mode); \
+    if (!pl.ok) {                                                                                   \
+        cpb::set_error("workspace too small: need %lld bytes, got %lld", (long long)pl.bytes,       \
+                       (long long)workspace_bytes);                                                 \
+        return CPB_ERR_WORKSPACE_TOO_SMALL;                                                         \
+    }                                                                                               \
+    VaeLayout L = make_layout(cfg->target_channels, cfg->z_dim);                                    \
+    cudaStream_t s = (cudaStream_t)stream;
+
+int32_t cpb_vae_encode(const cpb_vae_config* cfg, const float* params, const void* source, float* mean,
+                       float* logvar, int32_t* flags, void* workspace, int64_t workspace_bytes, void* stream) {
+    CPB_PLAN(CPB_WS_ENCODE);
+    CPB_REQUIRE(params && source && mean, "encode: NULL pointer");
+    CPB_TRY(relayout_weights(pl, L, params, false, false, s));
+    CPB_TRY(run_encoder(pl, L, cfg, params, source, flags, s));
+    const size_t n = (size_t)pl.B * pl.z * sizeof(float);
+    CPB_CUDA(cudaMemcpyAsync(mean, pl.heads, n, cudaMemcpyDeviceToDevice, s));
+    if (logvar) CPB_CUDA(cudaMemcpyAsync(logvar, pl.heads + (long long)pl.B * pl.z, n, cudaMemcpyDeviceToDevice, s));
+    return CPB_OK;
+}
+
+int32_t cpb_vae_decode(const cpb_vae_config* cfg, const float* params, const float* z, float* reconstruction,
+                       void* workspace, int64_t workspace_bytes, void* stream) {
+    CPB_PLAN(CPB_WS_FORWARD);
+    CPB_REQUIRE(params && z && reconstruction, "decode: NULL pointer");
+    CPB_TRY(relayout_weights(pl, L, params, true, false, s));
+    return run_decoder(pl, L, params, z, nullptr, reconstruction, s);
+}
+
+int32_t cpb_vae_forward(const cpb_vae_config* cfg, const float* params, const void* source, const void* target,
+                        const float* eps, float* losses, float* mean, float* logvar, float* z,
+                        float* reconstruction, int32_t* flags, void* workspace, int64_t workspace_bytes,
+                        void* stream) {
+    CPB_PLAN(CPB_WS_FORWARD);
+    CPB_REQUIRE(params && source && target && losses, "forward: NULL pointer");
+    CPB_TRY(relayout_weights(pl, L, params, true, false, s));
+    CPB_TRY(run_forward_loss(pl, L, cfg, params, source, target, eps, false, reconstruction, flags, s));
+    CPB_TRY(launch_finalize_losses(pl.frame_loss, pl.kl_rows, pl.B, cfg->loss_scale, losses, s));
+    const size_t n = (size_t)pl.B * pl.z * sizeof(float);
+    if (mean) CPB_CUDA(cudaMemcpyAsync(mean, pl.heads, n, cudaMemcpyDeviceToDevice, s));
+    if (logvar) CPB_CUDA(cudaMemcpyAsync(logvar, pl.heads + (long long)pl.B * pl.z, n, cudaMemcpyDeviceToDevice, s));
+    if (z) CPB_CUDA(cudaMemcpyAsync(z, pl.zbuf, n, cudaMemcpyDeviceToDevice, s));
+    return CPB_OK;
+}
+
+int32_t cpb_vae_loss_grad(const cpb_vae_config* cfg, const float* params, const void* source, const void* target,
+                          const float* eps, float* grads, float* losses, int32_t* flags, void* workspace,
+                          int64_t workspace_bytes, void* stream) {
+    CPB_PLAN(CPB_WS_TRAIN);
+    CPB_REQUIRE(params && source && target && grads && losses, "loss_grad: NULL pointer");
+    CPB_TRY(relayout_weights(pl, L, params, true, true, s));
+    CPB_TRY(run_forward_loss(pl, L, cfg, params, source, target, eps, true, nullptr, flags, s));
+    CPB_TRY(launch_finalize_losses(pl.frame_loss, pl.kl_rows, pl.B, cfg->loss_scale, losses, s));
+    return run_backward(pl, L, cfg, params, eps, grads, s);
+}
+
+int32_t cpb_adam_apply(float* params, const float* grads, float* m, float* v, int64_t n, float* powers, float lr,
+                       const float* lr_dev, float beta1, float beta2, float epsilon, void* stream) {
+    CPB_REQUIRE(params && grads && m && v && powers, "adam: NULL pointer");
+    return launch_adam(params, grads, m, v, n, powers, lr, lr_dev, beta1, beta2, epsilon, (cudaStream_t)stream);
+}
+
+int32_t cpb_vae_train_step(const cpb_vae_config* cfg, float* params, float* grads, float* adam_m, float* adam_v,
+                           float* adam_powers, float lr, const void* source, const void* target, const float* eps,
+                           float* losses, int32_t* flags, void* workspace, int64_t workspace_bytes, void* stream) {
+    CPB_TRY(cpb_vae_loss_grad(cfg, params, source, target, eps, grads, losses, flags, workspace, workspace_bytes, stream));
+    VaeLayout L = make_layout(cfg->target_channels, cfg->z_dim);
+    return cpb_adam_apply(params, grads, adam_m, adam_v, L.total, adam_powers, lr, nullptr, 0.9f, 0.999f, 1e-8f, stream);
+}
+
+static int64_t frame_bytes(int dtype, int channels) {
+    return (int64_t)geo::NPIX * channels * (dtype == CPB_FRAME_U8 ? 1 : 4);
+}
+
+int64_t cpb_vae_staging_bytes(const cpb_vae_config* cfg) {
+    if (check_cfg(cfg) != CPB_OK) return CPB_ERR_INVALID_ARGUMENT;
+    const int64_t b = cfg->batch;
+    return align_up(b * frame_bytes(cfg->source_dtype, 3), 256) +
+           align_up(b * frame_bytes(cfg->target_dtype, cfg->target_channels), 256) +
+           align_up(b * cfg->z_dim * 4, 256) + 256;
+}
+
+int32_t cpb_vae_train_step_host(const cpb_vae_config* cfg, float* params, float* grads, float* adam_m,
+                                float* adam_v, float* adam_powers, float lr, const void* source_host,
+                                const void* target_host, const float* eps_host, float* losses_host,
+                                int32_t* flags_host, void* staging, int64_t staging_bytes, void* workspace,
+                                int64_t workspace_bytes, void* stream) {
+    CPB_TRY(check_cfg(cfg));
+    CPB_REQUIRE(source_host && target_host && eps_host && losses_host && staging, "train_step_host: NULL pointer");
+    CPB_REQUIRE(staging_bytes >= cpb_vae_staging_bytes(cfg), "staging buffer too small");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t b = cfg->batch;
+    Arena a(staging, staging_bytes);
+    const int64_t sb = b * frame_bytes(cfg->source_dtype, 3);
+    const int64_t tb = b * frame_bytes(cfg->target_dtype, cfg->target_channels);
+    char* d_src = a.take<char>(sb);
+    char* d_tgt = a.take<char>(tb);
+    float* d_eps = a.take<float>(b * cfg->z_dim);
+    float* d_out = a.take<float>(4);   // losses[2], flags
+    CPB_CUDA(cudaMemcpyAsync(d_src, source_host, sb, cudaMemcpyHostToDevice, s));
+    const void* tgt = d_src;
+    if (target_host != source_host) {
+        CPB_CUDA(cudaMemcpyAsync(d_tgt, target_host, tb, cudaMemcpyHostToDevice, s));
+        tgt = d_tgt;
+    }
+    CPB_CUDA(cudaMemcpyAsync(d_eps, eps_host, b * cfg->z_dim * 4, cudaMemcpyHostToDevice, s));
+    CPB_CUDA(cudaMemsetAsync(d_out, 0, 16, s));
+    CPB_TRY(cpb_vae_train_step(cfg, params, grads, adam_m, adam_v, adam_powers, lr, d_src, tgt, d_eps, d_out,
+                               (int32_t*)(d_out + 2), workspace, workspace_bytes, stream));
+    float host_out[4];
+    CPB_CUDA(cudaMemcpyAsync(host_out, d_out, 16, cudaMemcpyDeviceToHost, s));
+    CPB_CUDA(cudaStreamSynchronize(s));
+    losses_host[0] = host_out[0];
+    losses_host[1] = host_out[1];
+    if (flags_host) memcpy(flags_host, &host_out[2], 4);
+    return CPB_OK;
+}
+
+}  // extern "C"

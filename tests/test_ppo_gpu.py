@@ -1,0 +1,146 @@
+"""GPU parity tests of the PPO update path (C ABI through the reference-shaped PPO class) against the
+float64 oracle.  Tolerance: ||x - ref|| / ||ref|| <= 1e-5 for forward quantities, losses and updated
+parameters; gradients <= max(2 x fp32-CPU-restatement error, 2e-5) per tensor."""
+import numpy as np
+import pytest
+
+from helpers import Box, rel_l2, shipped_ppo
+
+pytestmark = pytest.mark.gpu
+
+LOW, HIGH = np.array([-1.0, 0.0]), np.array([1.0, 1.0])
+TOL = 1e-5
+
+
+def make_ppo(tmp_path, policy=None, old=None, **kw):
+    from carla_ppo_b200.ppo import PPO
+    kw.setdefault("learning_rate", 1e-4)
+    kw.setdefault("value_scale", 1.0)
+    kw.setdefault("entropy_scale", 0.01)
+    kw.setdefault("epsilon", 0.2)
+    m = PPO((67,), Box(LOW, HIGH), model_dir=str(tmp_path / "ppo"), seed=0, **kw)
+    m.init_session(init_logging=False)
+    if policy is not None:
+        m.set_weights(policy, old if old is not None else policy)
+    return m
+
+
+def rollout(T, seed=0):
+    rs = np.random.RandomState(seed)
+    states = rs.randn(T, 67).astype(np.float32)
+    actions = np.clip(rs.randn(T, 2), LOW, HIGH).astype(np.float32)
+    rewards = rs.rand(T)
+    values = rs.randn(T).astype(np.float32)
+    dones = np.zeros(T, bool); dones[-1] = True
+    return states, actions, rewards, values, dones
+
+
+def test_predict_matches_oracle(tmp_path):
+    from oracle import ppo_oracle as po
+    pol, _ = shipped_ppo("policy")
+    m = make_ppo(tmp_path, pol)
+    states = rollout(33)[0]
+    p64 = {k: v.astype(np.float64) for k, v in pol.items()}
+    act, val = m.predict(states, greedy=True)
+    ract, rval = po.predict(p64, states, LOW, HIGH)
+    assert act.shape == (33, 2) and val.shape == (33,)
+    assert rel_l2(act, ract) < TOL and rel_l2(val, rval) < TOL
+    noise = np.random.RandomState(5).randn(33, 2)
+    act, _ = m.predict(states, noise=noise)
+    ract, _ = po.predict(p64, states, LOW, HIGH, noise=noise)
+    assert rel_l2(act, ract) < TOL
+    assert (act >= LOW - 1e-7).all() and (act <= HIGH + 1e-7).all()
+    a1, v1 = m.predict(states[0], greedy=True)              # B=1 squeeze (ppo.py:249-250)
+    assert a1.shape == (2,) and np.ndim(v1) == 0
+    assert rel_l2(a1, ract[0] * 0 + po.predict(p64, states[0], LOW, HIGH)[0]) < TOL
+
+
+@pytest.mark.parametrize("batch", [256, 37])
+def test_loss_and_gradients_match_oracle(tmp_path, batch):
+    import torch
+    from oracle import ppo_oracle as po, torch_ref
+    pol, _ = shipped_ppo("policy")
+    old, _ = shipped_ppo("policy_old")
+    m = make_ppo(tmp_path, pol, old)
+    rs = np.random.RandomState(1)
+    s, a = rollout(batch, 2)[:2]
+    ret = rs.randn(batch).astype(np.float32); adv = rs.randn(batch).astype(np.float32)
+    metrics, grads = m.loss_and_grads(s, a, ret, adv)
+    ref = po.loss_and_grads(pol, old, s, a, ret, adv, LOW, HIGH, 0.2, 1.0, 0.01)
+    ref32 = torch_ref.ppo_loss_and_grads(pol, old, s, a, ret, adv, LOW, HIGH, 0.2, 1.0, 0.01, dtype=torch.float32)
+    for got, key in zip(metrics, ("policy_loss", "value_loss", "entropy_loss", "loss", "mean_ratio")):
+        assert abs(got - ref[key]) <= TOL * max(abs(ref[key]), 1e-3), key
+    for name, g in ref["grads"].items():
+        err = rel_l2(grads[name], g)
+        tol = max(2 * rel_l2(ref32["grads"][name], g), 2e-5)
+        assert err < tol, "%s: %.3e (fp32 cpu %.3e)" % (name, err, tol / 2)
+
+
+def test_train_step_matches_oracle(tmp_path):
+    from oracle import ppo_oracle as po, vae_oracle as vo
+    pol, z = shipped_ppo("policy")
+    old, _ = shipped_ppo("policy_old")
+    m = make_ppo(tmp_path, pol, old)
+    s, a = rollout(64, 3)[:2]
+    rs = np.random.RandomState(4)
+    ret = rs.randn(64).astype(np.float32); adv = rs.randn(64).astype(np.float32)
+    p64 = {k: v.astype(np.float64) for k, v in pol.items()}
+    st = vo.adam_init_state(p64)
+    for _ in range(2):
+        m.train(s, a, ret, adv)
+        out = po.loss_and_grads(p64, old, s, a, ret, adv, LOW, HIGH, 0.2, 1.0, 0.01)
+        vo.adam_apply(p64, out["grads"], st, 1e-4)
+    got = m.get_weights()
+    for name in p64:
+        assert rel_l2(got[name], p64[name]) < TOL, name
+    assert m.get_train_step_idx() == 2
+
+
+def test_compute_gae_matches_reference_expression():
+    from carla_ppo_b200.utils import compute_gae
+    from oracle import ppo_oracle as po
+    rs = np.random.RandomState(0)
+    for T in (1, 5, 128, 2048, 2500):
+        r = rs.rand(T); v = rs.randn(T); d = rs.rand(T) < 0.05
+        got = compute_gae(list(r), list(v), 0.3, list(d), 0.99, 0.95)
+        ref = po.compute_gae(r, v, 0.3, d, 0.99, 0.95)
+        assert got.dtype == np.float64 and got.shape == (T,)
+        assert rel_l2(got, ref) < 1e-12, T
+
+
+def test_learn_matches_oracle_driver_block(tmp_path):
+    """BASELINE config 3 shape at reduced size for the oracle: T=512, 2 epochs x minibatch 96 (short tail),
+    shipped ckpt-705 weights; parameters after learn() vs the float64 restatement of train.py:171-207."""
+    from oracle import ppo_oracle as po, vae_oracle as vo
+    pol, _ = shipped_ppo("policy")
+    m = make_ppo(tmp_path, pol)
+    T, E, B = 512, 2, 96
+    s, a, r, v, d = rollout(T, 7)
+    perms = np.stack([np.random.RandomState(10 + e).permutation(T) for e in range(E)])
+    metrics = m.learn(s, a, v, r, d, 0.3, gamma=0.99, lam=0.95, num_epochs=E, batch_size=B, perms=perms, return_metrics=True)
+    p64 = {k: x.astype(np.float64) for k, x in pol.items()}
+    st = vo.adam_init_state(p64)
+    rec = po.learn(p64, st, s, a, v, r, d, 0.3, LOW, HIGH, 0.99, 0.95, 1e-4, 0.2, 1.0, 0.01, E, B, perms)
+    got = m.get_weights()
+    for name in p64:
+        assert rel_l2(got[name], p64[name]) < TOL, name
+    rec = np.asarray(rec)
+    assert metrics.shape == rec.shape
+    assert np.allclose(metrics[:, 3], rec[:, 3], rtol=2e-4, atol=1e-5)      # total loss of every minibatch
+    old = m.get_old_weights()
+    assert all(np.array_equal(old[k], pol[k]) for k in pol)                 # theta_old == theta at learn() entry
+    assert m.get_train_step_idx() == E * 6
+
+
+def test_checkpoint_round_trip_and_lr_decay(tmp_path):
+    pol, _ = shipped_ppo("policy")
+    m = make_ppo(tmp_path, pol, lr_decay=0.5)
+    assert abs(float(m.learning_rate) - 1e-4) < 1e-12
+    m.write_episodic_summaries()
+    assert m.get_episode_idx() == 1 and abs(float(m._lr_dev.item()) - 5e-5) < 1e-10
+    m.save()
+    m2 = make_ppo(tmp_path)
+    assert m2.load_latest_checkpoint() is True
+    assert m2.get_episode_idx() == 1
+    w1, w2 = m.get_weights(), m2.get_weights()
+    assert all(np.array_equal(w1[k], w2[k]) for k in w1)
