@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's benchmark contract for carla_ppo_b200.
+
+    python bench.py --gpus N --steps K --warmup W            (this build: sm_100a CUDA behind the C ABI)
+    python bench.py --impl reference --steps K --warmup W    (the reference's CPU path on the host cores)
+
+Metric (BASELINE.json): VAE frames/sec @ batch 4096 -- one "step" is one ConvVAE train step (forward +
+MSE/KL loss + backward + TF-Adam, parameters updated in place) on synthetic 160x80x3 frames, z_dim 64
+(BASELINE configs[1]); N>1 shards the SAME global batch of 4096 frames over N ranks (configs[3], strong
+scaling) with one NCCL all-reduce of the flat gradient per step.  Secondary object "ppo": the PPO update
+of configs[2] (T=2048 rollout, 4 epochs x 256 minibatch) in latent-updates/sec.
+
+One JSON line on stdout (rank 0).  Keys follow the contract: value = whole-job frames/s with inputs resident
+in HBM; e2e = the same step fed from pinned HOST buffers through the C-ABI host entry point (H2D of the frames
+and D2H of the losses inside the timed region); roofline = dominant kernel group vs measured peaks;
+cpu_baseline = torch-CPU fp32 restatement of the reference graph ("port": TensorFlow 1.13 cannot be installed).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+GLOBAL_BATCH = 4096
+Z_DIM = 64
+FLOP_PER_FRAME_TRAIN = 776_494_080
+BYTES_PER_FRAME_TRAIN = 10_164_000           # layer-materialised fp32 model, SURVEY.md section 8(d)
+
+# algorithmic MACs per frame of each labelled kernel group (x2 for FLOPs)
+MAC = {"conv1": 4_732_416, "conv2": 22_413_312, "conv3": 18_874_368, "conv4": 12_582_912,
+       "heads": 786_432, "dense1": 393_216, "deconv1": 12_582_912, "deconv2": 18_874_368,
+       "deconv3": 35_020_800, "deconv4": 4_732_416}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_burst=p["bf16_tflops"], bf16_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ================================================================================================== ours
+def make_vae(model_dir, data_parallel):
+    from carla_ppo_b200.vae.models import ConvVAE
+    vae = ConvVAE((80, 160, 3), z_dim=Z_DIM, beta=1.0, learning_rate=1e-4, loss_fn="mse", model_dir=model_dir,
+                  seed=0, data_parallel=data_parallel)
+    vae.init_session(init_logging=False)          # glorot-uniform random init of the reference architecture (seed 0)
+    return vae
+
+
+def profile_groups(lib, vae, x, eps, steps):
+    """Per-call-site device time (CUDA events on the launching stream) over `steps` extra steps."""
+    import torch
+    lib.cpb_profile_reset(); lib.cpb_profile_enable(1)
+    for _ in range(steps):
+        vae.train_step_device(x, x, eps)
+    torch.cuda.synchronize()
+    lib.cpb_profile_enable(0)
+    buf = C.create_string_buffer(1 << 16)
+    n = lib.cpb_profile_report(buf, len(buf))
+    lib.cpb_profile_reset()
+    groups = {}
+    for line in buf.raw[:n].decode().splitlines():
+        label, count, ms = line.split()
+        groups[label] = {"launch_groups": int(count) // 1, "ms_per_step": float(ms) / steps}
+    return groups
+
+
+def bench_ppo(steps=5):
+    """BASELINE configs[2]: T=2048 rollout of 67-d states, 4 epochs x 256 minibatch."""
+    import torch
+    from carla_ppo_b200.ppo import PPO
+
+    class Box:
+        low = np.array([-1.0, 0.0], np.float32); high = np.array([1.0, 1.0], np.float32); shape = (2,)
+    tmp = tempfile.mkdtemp()
+    ppo = PPO((67,), Box(), learning_rate=1e-4, value_scale=1.0, entropy_scale=0.01, epsilon=0.2, model_dir=tmp, seed=0)
+    ppo.init_session(init_logging=False)
+    T, E, B = 2048, 4, 256
+    rs = np.random.RandomState(0)
+    dev = ppo._device
+    s = torch.from_numpy(rs.randn(T, 67).astype(np.float32)).to(dev)
+    a = torch.from_numpy(np.clip(rs.randn(T, 2), Box.low, Box.high).astype(np.float32)).to(dev)
+    r = torch.from_numpy(rs.rand(T)).to(dev); v = torch.from_numpy(rs.randn(T)).to(dev)
+    d = torch.zeros(T, dtype=torch.float64, device=dev); d[-1] = 1
+    perms = torch.from_numpy(np.stack([np.random.RandomState(e).permutation(T) for e in range(E)]).astype(np.int32)).to(dev)
+    for _ in range(2):
+        ppo.learn(s, a, v, r, d, 0.3, num_epochs=E, batch_size=B, perms=perms)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        ppo.learn(s, a, v, r, d, 0.3, num_epochs=E, batch_size=B, perms=perms)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"metric": "PPO latent-updates/sec", "value": T * E / ms * 1e3, "unit": "sample-updates/s",
+            "ms_per_learn": ms, "config": {"workload": "T=2048 rollout x 67-d states, 4 epochs x 8 minibatches of 256, GAE+normalise+theta_old copy+32 Adam steps"}}
+
+
+def cpu_baseline_vae(seconds=12.0, micro=256):
+    """torch-CPU fp32 restatement of the reference train step on a bounded sample (micro-batches of 256)."""
+    import torch
+    from oracle.torch_ref import TorchVAETrainer
+    from oracle.vae_oracle import glorot_init
+    torch.set_num_threads(os.cpu_count() or 1)
+    tr = TorchVAETrainer(glorot_init(0), lr=1e-4, loss_type="mse")
+    g = torch.Generator(); g.manual_seed(0)
+    x = torch.rand(micro, 80, 160, 3, generator=g); eps = torch.randn(micro, Z_DIM, generator=g)
+    tr.step(x, x, eps)                                   # warm-up
+    n = 0
+    t0 = time.perf_counter()
+    while True:
+        tr.step(x, x, eps); n += 1
+        dt = time.perf_counter() - t0
+        if dt >= seconds or n >= 64:
+            break
+    return {"value": n * micro / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d full train steps (fwd+loss+bwd+TF-Adam) on micro-batches of %d synthetic frames, torch-CPU fp32 "
+                      "restatement of the TF-1.13 graph (TensorFlow itself is not installable here)" % (n, micro)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from carla_ppo_b200 import _lib
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _lib.load()
+    assert GLOBAL_BATCH % world == 0
+    B = GLOBAL_BATCH // world
+    tmp = tempfile.mkdtemp()
+    vae = make_vae(tmp, data_parallel=world > 1)
+    g = torch.Generator(device="cuda"); g.manual_seed(1234 + rank)
+    x = torch.rand(B, 80, 160, 3, generator=g, device="cuda")            # 629 MB at B=4096: larger than the 126 MB L2
+    eps = torch.randn(B, Z_DIM, generator=g, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        vae.train_step_device(x, x, eps)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lib.cpb_reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        vae.train_step_device(x, x, eps)
+    e1.record()
+    barrier()
+    launches = int(lib.cpb_launch_count())
+    elapsed = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
+    ms_step = float(elapsed.item()) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    value = GLOBAL_BATCH / ms_step * 1e3
+
+    # ---- e2e: the same step fed from pinned HOST memory through the reference-facing call
+    xh = torch.empty(B, 80, 160, 3, dtype=torch.float32).pin_memory(); xh.copy_(x.cpu())
+    eh = torch.empty(B, Z_DIM, dtype=torch.float32).pin_memory(); eh.copy_(eps.cpu())
+    h2d = xh.numel() * 4 + eh.numel() * 4
+    d2h = 12
+
+    def e2e_step():
+        if world == 1:
+            return vae.train_step(xh.numpy(), xh.numpy(), eh.numpy())          # cpb_vae_train_step_host
+        xd = xh.to("cuda", non_blocking=True); ed = eh.to("cuda", non_blocking=True)
+        return vae.train_step_device(xd, xd, ed).cpu()
+    e2e_steps = max(3, min(args.steps, 10))
+    e2e_step(); barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / e2e_steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = GLOBAL_BATCH / float(e2e_ms.item()) * 1e3
+
+    out = None
+    if rank == 0:
+        peaks = load_peaks()
+        groups = profile_groups(lib, vae, x, eps, 3) if world == 1 else {}
+        roof = None
+        if groups:
+            # dominant = the labelled conv/deconv kernel group with the largest share of the step
+            def flops(label):
+                layer, kind = label.split(".")
+                if layer not in MAC:
+                    return 0.0
+                return 2.0 * MAC[layer] * B
+            conv_like = {k: v for k, v in groups.items() if "." in k and k.split(".")[0] in MAC}
+            dom = max(conv_like, key=lambda k: conv_like[k]["ms_per_step"])
+            ach = flops(dom) / (conv_like[dom]["ms_per_step"] * 1e-3) / 1e12
+            total_ms = sum(v["ms_per_step"] for v in groups.values())
+            roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["bf16_sustained"], "traffic": None,
+                    "share_of_step": conv_like[dom]["ms_per_step"] / total_ms,
+                    "note": "fp32 SIMT FMA kernel (parity needs fp32-accurate math); peak quoted is the measured bf16 tensor "
+                            "figure (%s), fp32-FMA nominal peak is ~74 TFLOP/s" % peaks["source"],
+                    "step_hbm": {"bound": "hbm", "achieved": BYTES_PER_FRAME_TRAIN * GLOBAL_BATCH / (ms_step * 1e-3) / 1e9,
+                                 "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                 "frac": BYTES_PER_FRAME_TRAIN * GLOBAL_BATCH / (ms_step * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+                    "groups_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(groups.items(), key=lambda kv: -kv[1]["ms_per_step"])}}
+        cpu = cpu_baseline_vae() if (world == 1 and not args.no_cpu_baseline) else None
+        ppo = bench_ppo() if world == 1 else None
+        out = {"metric": "VAE frames/sec @ batch 4096", "value": value, "unit": "frames/s", "n_gpus": world,
+               "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+               "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": "ConvVAE train step (fwd + MSE/KL + bwd + TF-Adam), global batch 4096 x 160x80x3 -> 64-d latent "
+                                      "(BASELINE configs[1]%s)" % ("" if world == 1 else "; configs[3]: sharded %d/GPU, one NCCL all-reduce of the flat gradient" % B),
+                          "global_batch": GLOBAL_BATCH, "per_gpu_batch": B, "z_dim": Z_DIM, "loss": "mse", "lr": 1e-4,
+                          "weights": "glorot-uniform random init (reference architecture)",
+                          "l2": "inputs (629 MB/step at N=1) and activations (GBs) exceed the 126 MB L2; no explicit flush"},
+               "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+                       "ms_per_step": float(e2e_ms.item()), "steps": e2e_steps,
+                       "path": "cpb_vae_train_step_host (pinned fp32 frames H2D + losses D2H every step)" if world == 1 else
+                               "pinned host shard -> device copy -> train_step_device (+NCCL) -> losses D2H"},
+               "gpu_launches": launches, "clocks": clocks, "algorithmic_tflops": FLOP_PER_FRAME_TRAIN * GLOBAL_BATCH / (ms_step * 1e-3) / 1e12}
+        if roof:
+            out["roofline"] = roof
+        if cpu:
+            out["cpu_baseline"] = cpu
+        if ppo:
+            out["ppo"] = ppo
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if out is not None:
+        print(json.dumps(out))
+
+
+# ============================================================================================= reference arm
+def run_reference(args):
+    """The reference's own CPU implementation of the path: torch-CPU fp32 restatement of the TF-1.13 graph
+    (oracle/torch_ref.py, kind "port") with all host threads, each step a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle.torch_ref import TorchVAETrainer
+    from oracle.vae_oracle import glorot_init
+    torch.set_num_threads(os.cpu_count() or 1)
+    sample, micro = 512, 256
+    tr = TorchVAETrainer(glorot_init(0), lr=1e-4, loss_type="mse")
+    g = torch.Generator(); g.manual_seed(0)
+    x = torch.rand(sample, 80, 160, 3, generator=g); eps = torch.randn(sample, Z_DIM, generator=g)
+    for _ in range(max(1, min(args.warmup, 2))):
+        tr.step(x, x, eps, micro_batch=micro)
+    steps = max(1, min(args.steps, 20))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.step(x, x, eps, micro_batch=micro)
+    dt = time.perf_counter() - t0
+    value = steps * sample / dt
+    desc = ("each step = one optimiser step on a bounded sample of %d synthetic frames (2 gradient-accumulation micro-batches "
+            "of %d) instead of 4096; torch-CPU fp32 restatement of the reference's TF-1.13 graph (TensorFlow not installable)" % (sample, micro))
+    print(json.dumps({"impl": "reference", "metric": "VAE frames/sec @ batch 4096", "value": value, "unit": "frames/s",
+                      "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": max(1, min(args.warmup, 2)),
+                      "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                      "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": "ConvVAE train step (fwd + MSE/KL + bwd + TF-Adam), 160x80x3 -> 64-d latent; " + desc,
+                                 "global_batch": GLOBAL_BATCH, "z_dim": Z_DIM, "loss": "mse", "lr": 1e-4},
+                      "cpu_baseline": {"value": value, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port", "sample": desc},
+                      "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "gpu_launches": 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

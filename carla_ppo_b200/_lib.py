@@ -67,6 +67,9 @@ PROTOTYPES = {
                              _i32, _i32, _P, _P, _P, _i64, _P]),
     "cpb_launch_count": (_i64, []),
     "cpb_reset_launch_count": (None, []),
+    "cpb_profile_enable": (None, [_i32]),
+    "cpb_profile_reset": (None, []),
+    "cpb_profile_report": (_i64, [C.c_char_p, _i64]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -49,6 +49,21 @@ extern int64_t g_launches;
         if (_s != CPB_OK) return _s;  \
     } while (0)
 
+// ---- optional per-call-site timing (see cpb_profile_* in the header) ---------------------------
+extern bool g_profile_on;
+void profile_begin(const char* label, cudaStream_t s);
+void profile_end(cudaStream_t s);
+struct ProfScope {
+    cudaStream_t s;
+    bool on;
+    ProfScope(const char* label, cudaStream_t stream) : s(stream), on(g_profile_on) {
+        if (on) profile_begin(label, s);
+    }
+    ~ProfScope() {
+        if (on) profile_end(s);
+    }
+};
+
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

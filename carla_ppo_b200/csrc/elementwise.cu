@@ -423,6 +423,7 @@ int32_t launch_colsum(const float* g, long long rows, int pitch, int c_real, flo
                       cudaStream_t stream) {
     CPB_REQUIRE(pitch % 4 == 0, "colsum: pitch must be a multiple of 4");
     if (rows == 0) return CPB_OK;
+    ProfScope prof("bias_grad.colsum", stream);
     const long long rpb = colsum_rows_per_block(rows);
     const int nblocks = cdiv(rows, rpb);
     dim3 grid((unsigned)nblocks, (unsigned)cdiv(pitch / 4, 256));

@@ -20,6 +20,28 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+// ---- profiling -------------------------------------------------------------------------------
+bool g_profile_on = false;
+namespace {
+struct ProfRec { const char* label; cudaEvent_t a, b; };
+constexpr int kMaxProfRecs = 4096;
+ProfRec g_recs[kMaxProfRecs];
+int g_nrecs = 0;
+int g_open = -1;
+}
+void profile_begin(const char* label, cudaStream_t s) {
+    if (g_nrecs >= kMaxProfRecs) { g_open = -1; return; }
+    ProfRec& r = g_recs[g_nrecs];
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) { g_open = -1; return; }
+    r.label = label;
+    cudaEventRecord(r.a, s);
+    g_open = g_nrecs++;
+}
+void profile_end(cudaStream_t s) {
+    if (g_open >= 0) cudaEventRecord(g_recs[g_open].b, s);
+    g_open = -1;
+}
+
 static std::once_flag g_init_once;
 static int32_t g_init_status = CPB_OK;
 int32_t ensure_init() {
@@ -273,8 +295,15 @@ static TapGemmParams dense_problem(const float* src, int B, int K, const float* 
     return p;
 }
 
-static int32_t run_wgrad(const float* big, int Wb, int pitch, long long big_img, int k, const float* small, int B,
-                         int Ho, int Wo, int J, int c_pad, int c_real, float* partial, float* out, cudaStream_t s) {
+static int32_t tg(const char* label, const TapGemmParams& p, cudaStream_t s) {
+    ProfScope prof(label, s);
+    return launch_tapgemm(p, s);
+}
+
+static int32_t run_wgrad(const char* label, const float* big, int Wb, int pitch, long long big_img, int k,
+                         const float* small, int B, int Ho, int Wo, int J, int c_pad, int c_real, float* partial,
+                         float* out, cudaStream_t s) {
+    ProfScope prof(label, s);
     WgradParams w;
     memset(&w, 0, sizeof(w));
     w.big = big; w.small = small; w.partial = partial;
@@ -289,8 +318,9 @@ static int32_t run_wgrad(const float* big, int Wb, int pitch, long long big_img,
     return launch_reduce_partials(partial, w.splits, w.I, w.J, c_pad, c_real, out, s);
 }
 
-static int32_t run_dense_wgrad(const float* x, int K, const float* g, int B, int J, float* partial, float* out,
-                               cudaStream_t s) {
+static int32_t run_dense_wgrad(const char* label, const float* x, int K, const float* g, int B, int J, float* partial,
+                               float* out, cudaStream_t s) {
+    ProfScope prof(label, s);
     WgradParams w;
     memset(&w, 0, sizeof(w));
     w.big = x; w.small = g; w.partial = partial;
@@ -342,6 +372,7 @@ static int32_t relayout_weights(const VaePlan& pl, const VaeLayout& L, const flo
         add(L.off[T_MEAN_K], pl.rl.headsT, 2, FEAT, pl.z, 0, 0);   // mean and logvar kernels are adjacent
         add(L.off[T_DECONV4_K], pl.rl.deconv4P, 16, pl.ct, C1, 1, 4);
     }
+    ProfScope prof("relayout_weights", s);
     return launch_relayout(params, pl.relayout, t, s);
 }
 
@@ -350,23 +381,24 @@ static int32_t run_encoder(const VaePlan& pl, const VaeLayout& L, const cpb_vae_
     using namespace geo;
     const int B = pl.B;
     const float sscale = cfg->source_dtype == CPB_FRAME_U8 ? 1.f / 255.f : 1.f;
-    CPB_TRY(launch_prep_frames(source, cfg->source_dtype, sscale, 3, (long long)B * NPIX, pl.xp, flags, 1, s));
+    { ProfScope prof("prep_frames", s);
+      CPB_TRY(launch_prep_frames(source, cfg->source_dtype, sscale, 3, (long long)B * NPIX, pl.xp, flags, 1, s)); }
     TapGemmParams p = gather_problem(pl.xp, B, H0, W0, 4, 4, pl.relayout + pl.rl.conv1P, C1,
                                      params + L.off[T_CONV1_B], nullptr, pl.a1, 1);
-    CPB_TRY(launch_tapgemm(p, s));
+    CPB_TRY(tg("conv1.fwd", p, s));
     p = gather_problem(pl.a1, B, H1, W1, C1, 4, params + L.off[T_CONV2_K], C2, params + L.off[T_CONV2_B], nullptr, pl.a2, 1);
-    CPB_TRY(launch_tapgemm(p, s));
+    CPB_TRY(tg("conv2.fwd", p, s));
     p = gather_problem(pl.a2, B, H2, W2, C2, 4, params + L.off[T_CONV3_K], C3, params + L.off[T_CONV3_B], nullptr, pl.a3, 1);
-    CPB_TRY(launch_tapgemm(p, s));
+    CPB_TRY(tg("conv3.fwd", p, s));
     p = gather_problem(pl.a3, B, H3, W3, C3, 4, params + L.off[T_CONV4_K], C4, params + L.off[T_CONV4_B], nullptr, pl.a4, 1);
-    CPB_TRY(launch_tapgemm(p, s));
+    CPB_TRY(tg("conv4.fwd", p, s));
     // both heads as one y-batched dense problem: heads[0] = mean, heads[1] = logstd_sq
     p = dense_problem(pl.a4, B, FEAT, params + L.off[T_MEAN_K], pl.z, params + L.off[T_MEAN_B], nullptr, pl.heads, 0);
     p.ybatch = 2;
     p.w_ystride = L.off[T_LOGVAR_K] - L.off[T_MEAN_K];
     p.bias_ystride = L.off[T_LOGVAR_B] - L.off[T_MEAN_B];
     p.dst_ystride = (long long)B * pl.z;
-    return launch_tapgemm(p, s);
+    return tg("heads.fwd", p, s);
 }
 
 // zbuf -> d1 -> b1 -> b2 -> b3 -> (logits_p and/or sigmoid)
@@ -376,16 +408,17 @@ static int32_t run_decoder(const VaePlan& pl, const VaeLayout& L, const float* p
     const int B = pl.B;
     TapGemmParams p = dense_problem(zsrc, B, pl.z, params + L.off[T_DENSE1_K], FEAT, params + L.off[T_DENSE1_B],
                                     nullptr, pl.d1, 0);
-    CPB_TRY(launch_tapgemm(p, s));
+    CPB_TRY(tg("dense1.fwd", p, s));
     p = scatter_problem(pl.d1, B, H4, W4, C4, 4, pl.relayout + pl.rl.deconv1T, C3, params + L.off[T_DECONV1_B],
                         nullptr, pl.b1, H3, W3, 1);
-    CPB_TRY(launch_tapgemm(p, s));
+    CPB_TRY(tg("deconv1.fwd", p, s));
     p = scatter_problem(pl.b1, B, H3, W3, C3, 4, pl.relayout + pl.rl.deconv2T, C2, params + L.off[T_DECONV2_B],
                         nullptr, pl.b2, H2, W2, 1);
-    CPB_TRY(launch_tapgemm(p, s));
+    CPB_TRY(tg("deconv2.fwd", p, s));
     p = scatter_problem(pl.b2, B, H2, W2, C2, 5, pl.relayout + pl.rl.deconv3T, C1, params + L.off[T_DECONV3_B],
                         nullptr, pl.b3, H1, W1, 1);
-    CPB_TRY(launch_tapgemm(p, s));
+    CPB_TRY(tg("deconv3.fwd", p, s));
+    ProfScope prof("deconv4.fwd", s);
     return launch_deconv4_fwd(pl.b3, params + L.off[T_DECONV4_K], params + L.off[T_DECONV4_B], B, pl.ct, logits_p,
                               sigm, s);
 }
@@ -408,8 +441,9 @@ static int32_t run_forward_loss(const VaePlan& pl, const VaeLayout& L, const cpb
                                    pl.yp, flags, 2, s));
     }
     const float gscale = cfg->loss_scale / (float)B;
-    CPB_TRY(launch_recon_loss(pl.logits_p, yp, B, pl.ct, cfg->loss_type, gscale, pl.frame_loss,
-                              want_dlogits ? pl.logits_p : nullptr, s));
+    { ProfScope prof("recon_loss", s);
+      CPB_TRY(launch_recon_loss(pl.logits_p, yp, B, pl.ct, cfg->loss_type, gscale, pl.frame_loss,
+                                want_dlogits ? pl.logits_p : nullptr, s)); }
     return CPB_OK;
 }
 
@@ -422,40 +456,40 @@ static int32_t run_backward(const VaePlan& pl, const VaeLayout& L, const cpb_vae
     float* cs = pl.colsum;
     CPB_TRY(launch_fill_zero(grads, L.total, s));
     // ---- deconv4 (padded to 4 channels on the big side)
-    CPB_TRY(run_wgrad(dlog, W0, 4, (long long)NPIX * 4, 4, pl.b3, B, H1, W1, C1, 4, pl.ct, pl.partial,
+    CPB_TRY(run_wgrad("deconv4.wgrad", dlog, W0, 4, (long long)NPIX * 4, 4, pl.b3, B, H1, W1, C1, 4, pl.ct, pl.partial,
                       grads + L.off[T_DECONV4_K], s));
     CPB_TRY(launch_colsum(dlog, (long long)B * NPIX, 4, pl.ct, grads + L.off[T_DECONV4_B], cs, s));
     TapGemmParams p = gather_problem(dlog, B, H0, W0, 4, 4, pl.relayout + pl.rl.deconv4P, C1, nullptr, pl.b3, pl.gA, 0);
-    CPB_TRY(launch_tapgemm(p, s));                                   // gA = g(b3 pre-activation)
+    CPB_TRY(tg("deconv4.dgrad", p, s));                                   // gA = g(b3 pre-activation)
     // ---- deconv3
-    CPB_TRY(run_wgrad(pl.gA, W1, C1, (long long)H1 * W1 * C1, 5, pl.b2, B, H2, W2, C2, 5 * 5 * C1, 5 * 5 * C1,
+    CPB_TRY(run_wgrad("deconv3.wgrad", pl.gA, W1, C1, (long long)H1 * W1 * C1, 5, pl.b2, B, H2, W2, C2, 5 * 5 * C1, 5 * 5 * C1,
                       pl.partial, grads + L.off[T_DECONV3_K], s));
     CPB_TRY(launch_colsum(pl.gA, (long long)B * H1 * W1, C1, C1, grads + L.off[T_DECONV3_B], cs, s));
     p = gather_problem(pl.gA, B, H1, W1, C1, 5, params + L.off[T_DECONV3_K], C2, nullptr, pl.b2, pl.gB, 0);
-    CPB_TRY(launch_tapgemm(p, s));                                   // gB = g(b2)
+    CPB_TRY(tg("deconv3.dgrad", p, s));                                   // gB = g(b2)
     // ---- deconv2
-    CPB_TRY(run_wgrad(pl.gB, W2, C2, (long long)H2 * W2 * C2, 4, pl.b1, B, H3, W3, C3, 16 * C2, 16 * C2, pl.partial,
+    CPB_TRY(run_wgrad("deconv2.wgrad", pl.gB, W2, C2, (long long)H2 * W2 * C2, 4, pl.b1, B, H3, W3, C3, 16 * C2, 16 * C2, pl.partial,
                       grads + L.off[T_DECONV2_K], s));
     CPB_TRY(launch_colsum(pl.gB, (long long)B * H2 * W2, C2, C2, grads + L.off[T_DECONV2_B], cs, s));
     p = gather_problem(pl.gB, B, H2, W2, C2, 4, params + L.off[T_DECONV2_K], C3, nullptr, pl.b1, pl.gA, 0);
-    CPB_TRY(launch_tapgemm(p, s));                                   // gA = g(b1)
+    CPB_TRY(tg("deconv2.dgrad", p, s));                                   // gA = g(b1)
     // ---- deconv1
-    CPB_TRY(run_wgrad(pl.gA, W3, C3, (long long)H3 * W3 * C3, 4, pl.d1, B, H4, W4, C4, 16 * C3, 16 * C3, pl.partial,
+    CPB_TRY(run_wgrad("deconv1.wgrad", pl.gA, W3, C3, (long long)H3 * W3 * C3, 4, pl.d1, B, H4, W4, C4, 16 * C3, 16 * C3, pl.partial,
                       grads + L.off[T_DECONV1_K], s));
     CPB_TRY(launch_colsum(pl.gA, (long long)B * H3 * W3, C3, C3, grads + L.off[T_DECONV1_B], cs, s));
     p = gather_problem(pl.gA, B, H3, W3, C3, 4, params + L.off[T_DECONV1_K], C4, nullptr, nullptr, pl.gB, 0);
-    CPB_TRY(launch_tapgemm(p, s));                                   // gB = g(d1) [B, 6144]
+    CPB_TRY(tg("deconv1.dgrad", p, s));                                   // gB = g(d1) [B, 6144]
     // ---- dense1
-    CPB_TRY(run_dense_wgrad(pl.zbuf, z, pl.gB, B, FEAT, pl.partial, grads + L.off[T_DENSE1_K], s));
+    CPB_TRY(run_dense_wgrad("dense1.wgrad", pl.zbuf, z, pl.gB, B, FEAT, pl.partial, grads + L.off[T_DENSE1_K], s));
     CPB_TRY(launch_colsum(pl.gB, B, FEAT, FEAT, grads + L.off[T_DENSE1_B], cs, s));
     p = dense_problem(pl.gB, B, FEAT, pl.relayout + pl.rl.dense1T, z, nullptr, nullptr, pl.gz, 0);
-    CPB_TRY(launch_tapgemm(p, s));
+    CPB_TRY(tg("dense1.dgrad", p, s));
     // ---- sampling + KL
     CPB_TRY(launch_reparam_bwd(pl.heads, eps, pl.gz, pl.kl_active, B, z, cfg->beta * cfg->loss_scale / (float)B,
                                pl.gheads, s));
     // ---- heads
-    CPB_TRY(run_dense_wgrad(pl.a4, FEAT, pl.gheads, B, z, pl.partial, grads + L.off[T_MEAN_K], s));
-    CPB_TRY(run_dense_wgrad(pl.a4, FEAT, pl.gheads + (long long)B * z, B, z, pl.partial, grads + L.off[T_LOGVAR_K], s));
+    CPB_TRY(run_dense_wgrad("heads.wgrad", pl.a4, FEAT, pl.gheads, B, z, pl.partial, grads + L.off[T_MEAN_K], s));
+    CPB_TRY(run_dense_wgrad("heads.wgrad", pl.a4, FEAT, pl.gheads + (long long)B * z, B, z, pl.partial, grads + L.off[T_LOGVAR_K], s));
     CPB_TRY(launch_colsum(pl.gheads, B, z, z, grads + L.off[T_MEAN_B], cs, s));
     CPB_TRY(launch_colsum(pl.gheads + (long long)B * z, B, z, z, grads + L.off[T_LOGVAR_B], cs, s));
     p = dense_problem(pl.gheads, B, z, pl.relayout + pl.rl.headsT, FEAT, nullptr, pl.a4, pl.gA, 0);
@@ -463,27 +497,27 @@ static int32_t run_backward(const VaePlan& pl, const VaeLayout& L, const cpb_vae
     p.cls[0].taps[1].dy = p.cls[0].taps[1].dx = 0;
     p.cls[0].taps[1].src_off = (long long)B * z;
     p.cls[0].taps[1].w_off = (long long)z * FEAT;
-    CPB_TRY(launch_tapgemm(p, s));                                   // gA = g(a4 pre-activation)
+    CPB_TRY(tg("heads.dgrad", p, s));                                   // gA = g(a4 pre-activation)
     // ---- conv4
-    CPB_TRY(run_wgrad(pl.a3, W3, C3, (long long)H3 * W3 * C3, 4, pl.gA, B, H4, W4, C4, 16 * C3, 16 * C3, pl.partial,
+    CPB_TRY(run_wgrad("conv4.wgrad", pl.a3, W3, C3, (long long)H3 * W3 * C3, 4, pl.gA, B, H4, W4, C4, 16 * C3, 16 * C3, pl.partial,
                       grads + L.off[T_CONV4_K], s));
     CPB_TRY(launch_colsum(pl.gA, (long long)B * H4 * W4, C4, C4, grads + L.off[T_CONV4_B], cs, s));
     p = scatter_problem(pl.gA, B, H4, W4, C4, 4, pl.relayout + pl.rl.conv4T, C3, nullptr, pl.a3, pl.gB, H3, W3, 0);
-    CPB_TRY(launch_tapgemm(p, s));                                   // gB = g(a3)
+    CPB_TRY(tg("conv4.dgrad", p, s));                                   // gB = g(a3)
     // ---- conv3
-    CPB_TRY(run_wgrad(pl.a2, W2, C2, (long long)H2 * W2 * C2, 4, pl.gB, B, H3, W3, C3, 16 * C2, 16 * C2, pl.partial,
+    CPB_TRY(run_wgrad("conv3.wgrad", pl.a2, W2, C2, (long long)H2 * W2 * C2, 4, pl.gB, B, H3, W3, C3, 16 * C2, 16 * C2, pl.partial,
                       grads + L.off[T_CONV3_K], s));
     CPB_TRY(launch_colsum(pl.gB, (long long)B * H3 * W3, C3, C3, grads + L.off[T_CONV3_B], cs, s));
     p = scatter_problem(pl.gB, B, H3, W3, C3, 4, pl.relayout + pl.rl.conv3T, C2, nullptr, pl.a2, pl.gA, H2, W2, 0);
-    CPB_TRY(launch_tapgemm(p, s));                                   // gA = g(a2)
+    CPB_TRY(tg("conv3.dgrad", p, s));                                   // gA = g(a2)
     // ---- conv2
-    CPB_TRY(run_wgrad(pl.a1, W1, C1, (long long)H1 * W1 * C1, 4, pl.gA, B, H2, W2, C2, 16 * C1, 16 * C1, pl.partial,
+    CPB_TRY(run_wgrad("conv2.wgrad", pl.a1, W1, C1, (long long)H1 * W1 * C1, 4, pl.gA, B, H2, W2, C2, 16 * C1, 16 * C1, pl.partial,
                       grads + L.off[T_CONV2_K], s));
     CPB_TRY(launch_colsum(pl.gA, (long long)B * H2 * W2, C2, C2, grads + L.off[T_CONV2_B], cs, s));
     p = scatter_problem(pl.gA, B, H2, W2, C2, 4, pl.relayout + pl.rl.conv2T, C1, nullptr, pl.a1, pl.gB, H1, W1, 0);
-    CPB_TRY(launch_tapgemm(p, s));                                   // gB = g(a1)
+    CPB_TRY(tg("conv2.dgrad", p, s));                                   // gB = g(a1)
     // ---- conv1 (its input gradient is never used: the reference computes and discards it)
-    CPB_TRY(run_wgrad(pl.xp, W0, 4, (long long)NPIX * 4, 4, pl.gB, B, H1, W1, C1, 4, 3, pl.partial,
+    CPB_TRY(run_wgrad("conv1.wgrad", pl.xp, W0, 4, (long long)NPIX * 4, 4, pl.gB, B, H1, W1, C1, 4, 3, pl.partial,
                       grads + L.off[T_CONV1_K], s));
     CPB_TRY(launch_colsum(pl.gB, (long long)B * H1 * W1, C1, C1, grads + L.off[T_CONV1_B], cs, s));
     return CPB_OK;
@@ -502,6 +536,34 @@ const char* cpb_last_error(void) { return cpb::g_err; }
 const char* cpb_build_info(void) { return "carla_ppo_b200 0.1 (sm_100a, fp32 SIMT tap-GEMM)"; }
 int64_t cpb_launch_count(void) { return cpb::g_launches; }
 void cpb_reset_launch_count(void) { cpb::g_launches = 0; }
+
+void cpb_profile_enable(int32_t on) { cpb::g_profile_on = on != 0; }
+void cpb_profile_reset(void) {
+    for (int i = 0; i < cpb::g_nrecs; ++i) { cudaEventDestroy(cpb::g_recs[i].a); cudaEventDestroy(cpb::g_recs[i].b); }
+    cpb::g_nrecs = 0;
+    cpb::g_open = -1;
+}
+int64_t cpb_profile_report(char* buf, int64_t capacity) {
+    cudaDeviceSynchronize();
+    struct Agg { const char* label; int count; double ms; };
+    static Agg agg[256];
+    int nagg = 0;
+    for (int i = 0; i < cpb::g_nrecs; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, cpb::g_recs[i].a, cpb::g_recs[i].b) != cudaSuccess) continue;
+        int j = 0;
+        for (; j < nagg; ++j) if (strcmp(agg[j].label, cpb::g_recs[i].label) == 0) break;
+        if (j == nagg) { if (nagg == 256) continue; agg[nagg++] = Agg{cpb::g_recs[i].label, 0, 0.0}; }
+        agg[j].count++; agg[j].ms += ms;
+    }
+    int64_t off = 0;
+    for (int j = 0; j < nagg; ++j) {
+        int n = snprintf(buf + off, capacity > off ? (size_t)(capacity - off) : 0, "%s %d %.6f\n", agg[j].label, agg[j].count, agg[j].ms);
+        if (n < 0 || off + n >= capacity) break;
+        off += n;
+    }
+    return off;
+}
 
 int32_t cpb_vae_num_tensors(void) { return T_COUNT; }
 const char* cpb_vae_tensor_name(int32_t i) { return (i >= 0 && i < T_COUNT) ? kVaeNames[i] : nullptr; }
@@ -590,6 +652,7 @@ int32_t cpb_vae_loss_grad(const cpb_vae_config* cfg, const float* params, const 
 int32_t cpb_adam_apply(float* params, const float* grads, float* m, float* v, int64_t n, float* powers, float lr,
                        const float* lr_dev, float beta1, float beta2, float epsilon, void* stream) {
     CPB_REQUIRE(params && grads && m && v && powers, "adam: NULL pointer");
+    ProfScope prof("adam", (cudaStream_t)stream);
     return launch_adam(params, grads, m, v, n, powers, lr, lr_dev, beta1, beta2, epsilon, (cudaStream_t)stream);
 }
 

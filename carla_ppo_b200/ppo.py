@@ -368,7 +368,10 @@ class PPO:
         d = self._dev(np.asarray(dones, dtype=np.float64) if not isinstance(dones, torch.Tensor) else dones, torch.float64).reshape(t_len)
         if perms is None:
             perms = np.stack([np.random.permutation(t_len) for _ in range(num_epochs)]) if num_epochs else np.zeros((0, t_len))
-        p = self._dev(np.asarray(perms).reshape(num_epochs, t_len), torch.int32)
+        if isinstance(perms, torch.Tensor):
+            p = perms.to(self._device, torch.int32).reshape(num_epochs, t_len).contiguous()
+        else:
+            p = self._dev(np.asarray(perms).reshape(num_epochs, t_len), torch.int32)
         nmb = -(-t_len // batch_size)
         metrics = torch.empty(max(num_epochs * nmb, 1), 5, dtype=torch.float32, device=self._device)
         ws = self._workspace(min(batch_size, t_len), t_len)

@@ -202,6 +202,14 @@ int32_t cpb_ppo_learn(const cpb_ppo_config* cfg, float* params, float* params_ol
 int64_t cpb_launch_count(void);
 void    cpb_reset_launch_count(void);
 
+/* Optional per-call-site device timing (CUDA events recorded on the launching stream around each
+ * labelled kernel group, e.g. "conv2.fwd", "deconv3.wgrad").  Off by default; bench.py turns it on for a
+ * few extra steps AFTER the timed region to attribute the step time and compute the roofline figures.
+ * cpb_profile_report synchronises the device and writes lines "label count total_ms\n" into buf. */
+void    cpb_profile_enable(int32_t on);
+void    cpb_profile_reset(void);
+int64_t cpb_profile_report(char* buf, int64_t capacity);
+
 #ifdef __cplusplus
 }
 #endif

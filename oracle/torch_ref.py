@@ -188,8 +188,8 @@ def ppo_loss_and_grads(params, params_old, s, a, ret, adv, low, high, epsilon=0.
     loss, (pl, vl, el, mr) = ppo_loss(p, po, _t(s, dtype), _t(a, dtype), _t(ret, dtype), _t(adv, dtype),
                                       _t(low, dtype), _t(high, dtype), epsilon, value_scale, entropy_scale)
     loss.backward()
-    return dict(loss=float(loss), policy_loss=float(pl), value_loss=float(vl), entropy_loss=float(el),
-                mean_ratio=float(mr), grads={k: v.grad.numpy() for k, v in p.items()})
+    return dict(loss=float(loss.detach()), policy_loss=float(pl.detach()), value_loss=float(vl.detach()), entropy_loss=float(el.detach()),
+                mean_ratio=float(mr.detach()), grads={k: v.grad.numpy() for k, v in p.items()})
 
 
 class TorchPPOLearner:

@@ -135,7 +135,7 @@ def test_learn_matches_oracle_driver_block(tmp_path):
 def test_checkpoint_round_trip_and_lr_decay(tmp_path):
     pol, _ = shipped_ppo("policy")
     m = make_ppo(tmp_path, pol, lr_decay=0.5)
-    assert abs(float(m.learning_rate) - 1e-4) < 1e-12
+    assert abs(float(m.learning_rate) - 1e-4) < 1e-11          # float32(1e-4), like the TF tensor
     m.write_episodic_summaries()
     assert m.get_episode_idx() == 1 and abs(float(m._lr_dev.item()) - 5e-5) < 1e-10
     m.save()
