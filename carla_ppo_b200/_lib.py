@@ -65,6 +65,10 @@ PROTOTYPES = {
     "cpb_gae": (_i32, [_P, _P, _f64, _P, _i32, _f64, _f64, _P, _P, _P, _P]),
     "cpb_ppo_learn": (_i32, [_PC, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _f64, _P, _i32, _f64, _f64,
                              _i32, _i32, _P, _P, _P, _i64, _P]),
+    "cpb_set_math_mode": (_i32, [_i32]),
+    "cpb_debug_vae_buffer_offsets": (_i32, [_i32, _i32, _i32, _i32, _P, _i32]),
+    "cpb_debug_tc_gemm": (_i32, [_P, _P, _P, _i32, _i32, _i32, _P, _P]),
+    "cpb_get_math_mode": (_i32, []),
     "cpb_launch_count": (_i64, []),
     "cpb_reset_launch_count": (None, []),
     "cpb_profile_enable": (None, [_i32]),

@@ -54,6 +54,14 @@ struct TapGemmParams {
     int nclass;           // 1 or 4
     int ybatch;           // independent problems sharing src (fused heads): 1 or 2
     long long w_ystride, bias_ystride, dst_ystride;
+    // tensor-core path only: K-major per-tap [N][C] weight blocks, pre-split into hi / lo (tc_tapgemm.cu)
+    const float* wk_hi;
+    const float* wk_lo;
+    // tensor-core path only: quad-fused scatter form.  One GEMM row = one 2x2 output quad (qy, qx); the N axis is
+    // (parity class, cb) = 4*quad_cb columns; cls[0] holds the union window taps (2x2 for k=4, 3x3 for k=5) and the
+    // weight blocks carry zeros where a class does not use a tap.  The A tile is loaded once for all four classes.
+    int quad;
+    int quad_cb;
     TapClass cls[4];
 };
 
@@ -61,5 +69,25 @@ struct TapGemmParams {
 int32_t launch_tapgemm(const TapGemmParams& p, cudaStream_t stream);
 // One-time opt-in for >48 KB dynamic shared memory (called from the API layer).
 int32_t tapgemm_init();
+
+// ---- tcgen05 (3xTF32) variant of the same contraction -------------------------------------------------
+struct TcWeightJob {
+    long long src_off;          // float offset of the TF kernel [k,k,Cb,Cs] in the parameter buffer
+    long long dst_hi, dst_lo;   // float offsets in the tensor-core weight buffer
+    int mode;                   // 0: plain copy; 1: gather form [kh][cs][kw*Cb+cb];
+                                // 2: quad scatter form [j][i][class*Cb+cb][cs], window w = (k+1)/2, zero where unused
+    int k, cb, cs;
+    long long count;
+};
+constexpr int kMaxTcWeightJobs = 12;
+struct TcWeightTable {
+    int njobs;
+    long long total;
+    TcWeightJob jobs[kMaxTcWeightJobs];
+};
+int32_t tc_tapgemm_init();
+bool tc_tapgemm_supported(const TapGemmParams& p);
+int32_t launch_tc_tapgemm(const TapGemmParams& p, cudaStream_t stream);
+int32_t launch_tc_weights(const float* params, float* dst, const TcWeightTable& table, cudaStream_t stream);
 
 }  // namespace cpb

@@ -1,0 +1,265 @@
+// Tensor-core weight gradient for sm_100a (tf Conv2DBackpropFilter for conv and transposed-conv layers):
+//
+//   gw[i, j] = sum_{m}  big[row(m) + tap_off[i / run] + i % run] * small[m * J + j]        (same contract as wgrad.cu)
+//
+// as D[128 x BN] += A^T B with the REDUCTION index m on the MMA K axis.  Both operands are activations / gradients
+// (nothing can be pre-split), and in NHWC memory the channel index -- not m -- is contiguous, so the loader
+// transposes on the fly: lane = reduction position (32 per k-block), each thread reads float4s of 4 channels for
+// its position, splits them into TF32 hi / lo parts, and scatters 4-byte stores into the K-major SWIZZLE_128B
+// tiles (for a fixed channel row the 32 lanes fill one 128-byte row: conflict-free).  MMA issue, the 3xTF32
+// products, the separate cross-term tile and the chunked drain into fp32 register accumulators are those of
+// tc_tapgemm.cu.  Each (i-tile, j-tile, split) CTA writes its partial [128 x BN] block; reduce_partials() sums the
+// splits in a fixed order (deterministic).
+#include "tc_common.cuh"
+#include "wgrad.cuh"
+
+namespace cpb {
+
+namespace {
+
+using namespace tc;
+
+constexpr int CHUNK_KB = 4;
+
+template <int BN>
+struct TcWgCfg {
+    static constexpr int B_TILE_BYTES = BN * TBK * 4;
+    static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+    static constexpr int STAGES = (STAGE_BYTES * 4 <= 200 * 1024) ? 4 : 3;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+    static constexpr int TMEM_COLS = BN == 128 ? 512 : (BN == 64 ? 256 : 128);
+};
+
+// byte offset of element (row, k) of a K-major SWIZZLE_128B tile (rows of 32 floats)
+__device__ __forceinline__ uint32_t sw_off(int row, int k) {
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 2) ^ (row & 7))) << 4) + (k & 3) * 4);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
+    using Cfg = TcWgCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr int B_TILE_BYTES = Cfg::B_TILE_BYTES;
+    constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
+    constexpr int BG = BN / 32;                       // float4 column groups of B per warp
+    static_assert(STAGES <= CHUNK_KB, "late drain relies on the stage ring being no deeper than a chunk");
+
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t empty_bar[STAGES];
+    __shared__ uint64_t chunk_bar[2];
+    __shared__ uint64_t done_bar;
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int i0 = blockIdx.x * TBM;
+    const int j0 = blockIdx.y * BN;
+    const int HoWo = p.Ho * p.Wo;
+    const long long M = (long long)p.batch * HoWo;
+    const long long m_begin = (long long)blockIdx.z * p.m_per_split;
+    long long m_end = m_begin + p.m_per_split;
+    if (m_end > M) m_end = M;
+    const int nkb = m_end > m_begin ? (int)((m_end - m_begin + TBK - 1) / TBK) : 0;
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(&empty_bar[s], 1);
+        mbar_init(&chunk_bar[0], 1);
+        mbar_init(&chunk_bar[1], 1);
+        mbar_init(&done_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc<Cfg::TMEM_COLS>(&tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    // ---- loader columns of this thread (fixed): A rows (warp*16 + g*4 .. +3), B rows (warp*BN/8 + g*4 .. +3)
+    long long a_coloff[4];
+    bool a_col_ok[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int i = i0 + (warp * 4 + g) * 4;
+        a_col_ok[g] = i < p.I;
+        a_coloff[g] = 0;
+        if (a_col_ok[g]) {
+            const int tap = i / p.run;
+            a_coloff[g] = p.tap_off[tap] + (i - tap * p.run);
+        }
+    }
+
+    float4 areg[4], breg[BG];
+    auto load_regs = [&](int kb) {
+        const long long m = m_begin + (long long)kb * TBK + lane;
+        const bool v = m < m_end;
+        long long base = 0;
+        if (v) {
+            const int n = (int)(m / HoWo);
+            const int rem = (int)(m - (long long)n * HoWo);
+            const int oy = rem / p.Wo;
+            const int ox = rem - oy * p.Wo;
+            base = (long long)n * p.big_img + ((long long)(oy * p.sstride) * p.Wb + ox * p.sstride) * p.big_pitch;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+            areg[g] = (v && a_col_ok[g]) ? __ldg(reinterpret_cast<const float4*>(p.big + base + a_coloff[g])) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int g = 0; g < BG; ++g)
+            breg[g] = v ? __ldg(reinterpret_cast<const float4*>(p.small + m * p.J + j0 + (warp * BG + g) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+
+    auto store4 = [&](uint32_t tile_hi, uint32_t tile_lo, int row0, const float4& x) {
+        const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float hi, lo;
+            split_tf32(xv[c], hi, lo);
+            const uint32_t o = sw_off(row0 + c, lane);
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(tile_hi + o), "f"(hi) : "memory");
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(tile_lo + o), "f"(lo) : "memory");
+        }
+    };
+
+    constexpr int HALF_COLS = BN / 2;
+    const int q = warp & 3;
+    const int half = warp >> 2;
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * HALF_COLS);
+    float acc[HALF_COLS];
+#pragma unroll
+    for (int i = 0; i < HALF_COLS; ++i) acc[i] = 0.f;
+    const int nchunks = (nkb + CHUNK_KB - 1) / CHUNK_KB;
+    int drained = 0;
+    auto drain_one = [&]() {
+        const int b = drained & 1;
+        mbar_wait(&chunk_bar[b], (uint32_t)((drained >> 1) & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int cc = 0; cc < HALF_COLS; cc += 16) {
+            float v[16];
+            tmem_ld16(tmem_lane + (uint32_t)(b * BN + cc), v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[cc + i] += v[i];
+        }
+        tc_fence_before();
+        ++drained;
+    };
+
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+    if (nkb > 0) load_regs(0);
+
+    for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t stage = smem_base + s * STAGE_BYTES;
+        if (kb >= STAGES) mbar_wait(&empty_bar[s], (uint32_t)((kb / STAGES - 1) & 1));
+        if (kb % CHUNK_KB == 0) {
+            while (drained < kb / CHUNK_KB - 1) drain_one();
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) store4(stage, stage + A_TILE_BYTES, (warp * 4 + g) * 4, areg[g]);
+#pragma unroll
+        for (int g = 0; g < BG; ++g)
+            store4(stage + 2 * A_TILE_BYTES, stage + 2 * A_TILE_BYTES + B_TILE_BYTES, (warp * BG + g) * 4, breg[g]);
+        if (kb + 1 < nkb) load_regs(kb + 1);
+
+        fence_async_smem();
+        __syncthreads();
+
+        if (tid == 0) {
+            tc_fence_after();
+            const uint64_t a_hi = make_desc(stage);
+            const uint64_t a_lo = make_desc(stage + A_TILE_BYTES);
+            const uint64_t b_hi = make_desc(stage + 2 * A_TILE_BYTES);
+            const uint64_t b_lo = make_desc(stage + 2 * A_TILE_BYTES + B_TILE_BYTES);
+            const int chunk = kb / CHUNK_KB;
+            const uint32_t d_main = tmem_base + (uint32_t)((chunk & 1) * BN);
+            const uint32_t d_cross = tmem_base + (uint32_t)(2 * BN);
+#pragma unroll
+            for (int ks = 0; ks < TBK / 8; ++ks) {
+                const uint64_t adv = (uint64_t)(ks * 2);
+                umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, ((kb % CHUNK_KB) | ks) != 0 ? 1u : 0u);
+                umma_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
+                umma_tf32(d_cross, a_hi + adv, b_lo + adv, idesc, 1u);
+            }
+            umma_commit(&empty_bar[s]);
+            if (kb % CHUNK_KB == CHUNK_KB - 1 || kb == nkb - 1) umma_commit(&chunk_bar[chunk & 1]);
+            if (kb == nkb - 1) umma_commit(&done_bar);
+        }
+    }
+
+    if (nkb > 0) {
+        while (drained < nchunks) drain_one();
+        mbar_wait(&done_bar, 0);
+        tc_fence_after();
+#pragma unroll
+        for (int cc = 0; cc < HALF_COLS; cc += 16) {
+            float v[16];
+            tmem_ld16(tmem_lane + (uint32_t)(2 * BN + cc), v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[cc + i] += v[i];
+        }
+    }
+    // ---- partial[split][i][j]
+    {
+        const int i = i0 + q * 32 + lane;
+        if (i < p.I) {
+            float* out = p.partial + ((long long)blockIdx.z * p.I + i) * p.J + j0 + half * HALF_COLS;
+#pragma unroll
+            for (int g = 0; g < HALF_COLS / 4; ++g)
+                *reinterpret_cast<float4*>(out + g * 4) = make_float4(acc[g * 4 + 0], acc[g * 4 + 1], acc[g * 4 + 2], acc[g * 4 + 3]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+template <int BN>
+int32_t tc_wg_launch(const WgradParams& p, cudaStream_t stream) {
+    dim3 grid((unsigned)cdiv(p.I, TBM), (unsigned)(p.J / BN), (unsigned)p.splits);
+    tc_wgrad_kernel<BN><<<grid, 256, TcWgCfg<BN>::SMEM_BYTES, stream>>>(p);
+    CPB_LAUNCHED();
+    return CPB_OK;
+}
+
+template <int BN>
+int32_t tc_wg_init_one() {
+    CPB_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcWgCfg<BN>::SMEM_BYTES));
+    return CPB_OK;
+}
+
+int tc_wg_bn(int J) { return J % 128 == 0 ? 128 : (J % 64 == 0 ? 64 : 32); }
+
+}  // namespace
+
+int32_t tc_wgrad_init() {
+    CPB_TRY(tc_wg_init_one<32>());
+    CPB_TRY(tc_wg_init_one<64>());
+    CPB_TRY(tc_wg_init_one<128>());
+    return CPB_OK;
+}
+
+bool tc_wgrad_supported(int I, int J, int run) { return run % 4 == 0 && J % 32 == 0 && I >= 128; }
+
+int tc_wgrad_pick_splits(int I, int J, long long M) {
+    const long long tiles = (long long)cdiv(I, TBM) * (J / tc_wg_bn(J));
+    long long splits = (148 + tiles - 1) / tiles;          // one CTA per SM (192 KB of shared memory each)
+    const long long max_splits = (M + 1023) / 1024;         // keep >= 1024 reduction positions per split
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    return (int)splits;
+}
+
+int32_t launch_tc_wgrad(const WgradParams& p, cudaStream_t stream) {
+    CPB_REQUIRE(tc_wgrad_supported(p.I, p.J, p.run) && p.I == p.ntaps * p.run, "tc_wgrad: unsupported problem (I=%d J=%d)", p.I, p.J);
+    CPB_REQUIRE(p.m_per_split % TBK == 0 && p.splits >= 1, "tc_wgrad: bad split");
+    switch (tc_wg_bn(p.J)) {
+        case 128: return tc_wg_launch<128>(p, stream);
+        case 64: return tc_wg_launch<64>(p, stream);
+        default: return tc_wg_launch<32>(p, stream);
+    }
+}
+
+}  // namespace cpb

@@ -42,12 +42,15 @@ void profile_end(cudaStream_t s) {
     g_open = -1;
 }
 
+int g_math_mode = 1;   // 0: fp32 SIMT everywhere; 1: 3xTF32 tcgen05 for the dense conv/deconv layers
 static std::once_flag g_init_once;
 static int32_t g_init_status = CPB_OK;
 int32_t ensure_init() {
     std::call_once(g_init_once, [] {
         g_init_status = tapgemm_init();
         if (g_init_status == CPB_OK) g_init_status = wgrad_init();
+        if (g_init_status == CPB_OK) g_init_status = tc_tapgemm_init();
+        if (g_init_status == CPB_OK) g_init_status = tc_wgrad_init();
     });
     return g_init_status;
 }
@@ -128,10 +131,13 @@ static VaeLayout make_layout(int ct, int z) {
 // ---------------------------------------------------------------------------------------------
 // workspace plan
 // ---------------------------------------------------------------------------------------------
+struct TcW { int64_t f_hi, f_lo, t_hi, t_lo; };   // gather-form / quad-scatter-form K-major hi/lo copies of one kernel
 struct Relayout {
     int64_t conv2T, conv3T, conv4T, deconv1T, deconv2T, deconv3T, dense1T, headsT, conv1P, deconv4P;
+    TcW tc[6];          // conv2, conv3, conv4, deconv1, deconv2, deconv3
     int64_t total;
 };
+enum { TC_CONV2, TC_CONV3, TC_CONV4, TC_DECONV1, TC_DECONV2, TC_DECONV3 };
 
 static Relayout make_relayout(int z) {
     using namespace geo;
@@ -148,6 +154,12 @@ static Relayout make_relayout(int z) {
     r.headsT = take(2LL * z * FEAT);
     r.conv1P = take(16LL * 4 * C1);
     r.deconv4P = take(16LL * 4 * C1);
+    const int64_t sizes[6] = {16LL * C1 * C2, 16LL * C2 * C3, 16LL * C3 * C4, 16LL * C3 * C4, 16LL * C2 * C3, 25LL * C1 * C2};
+    const int64_t qsizes[6] = {16LL * C1 * C2, 16LL * C2 * C3, 16LL * C3 * C4, 16LL * C3 * C4, 16LL * C2 * C3, 36LL * C1 * C2};
+    for (int i = 0; i < 6; ++i) {
+        r.tc[i].f_hi = take(sizes[i]); r.tc[i].f_lo = take(sizes[i]);
+        r.tc[i].t_hi = take(qsizes[i]); r.tc[i].t_lo = take(qsizes[i]);
+    }
     r.total = o;
     return r;
 }
@@ -177,6 +189,8 @@ static int64_t max_partial_floats(int B, int z) {
     int64_t best = 0;
     for (const P& p : ps) {
         int64_t n = (int64_t)wgrad_pick_splits(p.I, p.J, p.M) * p.I * p.J;
+        if (n > best) best = n;
+        n = (int64_t)tc_wgrad_pick_splits(p.I, p.J, p.M) * p.I * p.J;
         if (n > best) best = n;
     }
     return best;
@@ -236,8 +250,10 @@ static TapGemmParams base_params() {
 
 // gather form: small[b,i,j,:] = sum_{kh,kw,cb} big[b,2i+kh,2j+kw,cb] * W[kh,kw,cb,:]
 static TapGemmParams gather_problem(const float* big, int B, int Hb, int Wb, int pitch, int k, const float* W,
-                                    int N, const float* bias, const float* mask, float* small, int relu) {
+                                    int N, const float* bias, const float* mask, float* small, int relu,
+                                    const float* wk_hi = nullptr, const float* wk_lo = nullptr) {
     TapGemmParams p = base_params();
+    p.wk_hi = wk_hi; p.wk_lo = wk_lo;
     p.src = big; p.wmat = W; p.bias = bias; p.mask = mask; p.dst = small;
     p.batch = B; p.Hs = Hb; p.Ws = Wb; p.src_pitch = pitch; p.src_img = (long long)Hb * Wb * pitch;
     p.sstride = 2; p.C = k * pitch; p.N = N; p.ldw = N;
@@ -257,8 +273,9 @@ static TapGemmParams gather_problem(const float* big, int B, int Hb, int Wb, int
 // scatter form: big[b,2i+kh,2j+kw,cb] += small[b,i,j,cs] * W[kh,kw,cb,cs]; Wt is [kh][kw][cs][cb]
 static TapGemmParams scatter_problem(const float* small, int B, int Hs, int Ws, int Cs, int k, const float* Wt,
                                      int Cb, const float* bias, const float* mask, float* big, int Hb, int Wb,
-                                     int relu) {
+                                     int relu, const float* wk_hi = nullptr, const float* wk_lo = nullptr) {
     TapGemmParams p = base_params();
+    p.wk_hi = wk_hi; p.wk_lo = wk_lo;
     p.src = small; p.wmat = Wt; p.bias = bias; p.mask = mask; p.dst = big;
     p.batch = B; p.Hs = Hs; p.Ws = Ws; p.src_pitch = Cs; p.src_img = (long long)Hs * Ws * Cs;
     p.sstride = 1; p.C = Cs; p.N = Cb; p.ldw = Cb;
@@ -295,8 +312,37 @@ static TapGemmParams dense_problem(const float* src, int B, int K, const float* 
     return p;
 }
 
-static int32_t tg(const char* label, const TapGemmParams& p, cudaStream_t s) {
+// Re-express a 4-class scatter-form problem as ONE quad-fused GEMM (tensor-core path): rows = 2x2 output quads,
+// columns = (class, cb), taps = the union window; needs the mode-2 weights of tc_weights_kernel.
+static TapGemmParams quad_from_scatter(const TapGemmParams& sp, int k) {
+    TapGemmParams p = sp;
+    const int Cb = sp.N, Cs = sp.C;
+    p.quad = 1; p.quad_cb = Cb; p.N = 4 * Cb; p.nclass = 1; p.check = 1;
+    TapClass& c = p.cls[0];
+    const int win = (k + 1) / 2;
+    c.py = c.px = 0;
+    c.Ho = (sp.Hd + 1) / 2; c.Wo = (sp.Wd + 1) / 2;
+    c.ntaps = win * win;
+    for (int j = 0; j < win; ++j)
+        for (int i = 0; i < win; ++i) {
+            Tap& t = c.taps[j * win + i];
+            t.dy = -j; t.dx = -i;
+            t.src_off = ((long long)(-j) * sp.Ws - i) * Cs;
+            t.w_off = (long long)(j * win + i) * 4 * Cb * Cs;
+        }
+    return p;
+}
+
+static int32_t tg(const char* label, const TapGemmParams& p, cudaStream_t s, int scatter_k = 0) {
     ProfScope prof(label, s);
+    if (g_math_mode == 1) {
+        if (scatter_k > 0 && p.wk_hi != nullptr) {
+            const TapGemmParams q = quad_from_scatter(p, scatter_k);
+            if (tc_tapgemm_supported(q)) return launch_tc_tapgemm(q, s);
+        } else if (tc_tapgemm_supported(p)) {
+            return launch_tc_tapgemm(p, s);
+        }
+    }
     return launch_tapgemm(p, s);
 }
 
@@ -312,9 +358,15 @@ static int32_t run_wgrad(const char* label, const float* big, int Wb, int pitch,
     for (int kh = 0; kh < k; ++kh) w.tap_off[kh] = (long long)kh * Wb * pitch;
     w.I = k * k * pitch; w.J = J;
     const long long M = (long long)B * Ho * Wo;
-    w.splits = wgrad_pick_splits(w.I, w.J, M);
-    w.m_per_split = align_up((M + w.splits - 1) / w.splits, 16);
-    CPB_TRY(launch_wgrad(w, s));
+    if (g_math_mode == 1 && tc_wgrad_supported(w.I, w.J, w.run)) {
+        w.splits = tc_wgrad_pick_splits(w.I, w.J, M);
+        w.m_per_split = align_up((M + w.splits - 1) / w.splits, 32);
+        CPB_TRY(launch_tc_wgrad(w, s));
+    } else {
+        w.splits = wgrad_pick_splits(w.I, w.J, M);
+        w.m_per_split = align_up((M + w.splits - 1) / w.splits, 16);
+        CPB_TRY(launch_wgrad(w, s));
+    }
     return launch_reduce_partials(partial, w.splits, w.I, w.J, c_pad, c_real, out, s);
 }
 
@@ -373,7 +425,34 @@ static int32_t relayout_weights(const VaePlan& pl, const VaeLayout& L, const flo
         add(L.off[T_DECONV4_K], pl.rl.deconv4P, 16, pl.ct, C1, 1, 4);
     }
     ProfScope prof("relayout_weights", s);
-    return launch_relayout(params, pl.relayout, t, s);
+    CPB_TRY(launch_relayout(params, pl.relayout, t, s));
+    if (g_math_mode != 1) return CPB_OK;
+    TcWeightTable w;
+    memset(&w, 0, sizeof(w));
+    auto addw = [&](int tensor, int slot, int k, int cb, int cs, bool gather, bool scatter) {
+        const long long n = (long long)k * k * cb * cs;
+        if (gather) {
+            TcWeightJob& j = w.jobs[w.njobs++];
+            j.src_off = L.off[tensor]; j.dst_hi = pl.rl.tc[slot].f_hi; j.dst_lo = pl.rl.tc[slot].f_lo;
+            j.mode = 1; j.k = k; j.cb = cb; j.cs = cs; j.count = n; w.total += n;
+        }
+        if (scatter) {
+            TcWeightJob& j = w.jobs[w.njobs++];
+            j.src_off = L.off[tensor]; j.dst_hi = pl.rl.tc[slot].t_hi; j.dst_lo = pl.rl.tc[slot].t_lo;
+            const int win = (k + 1) / 2;
+            j.mode = 2; j.k = k; j.cb = cb; j.cs = cs; j.count = (long long)win * win * 4 * cb * cs; w.total += j.count;
+        }
+    };
+    // conv layers run gather-form forward / scatter-form dgrad; deconv layers the other way round
+    addw(T_CONV2_K, TC_CONV2, 4, C1, C2, true, backward);
+    addw(T_CONV3_K, TC_CONV3, 4, C2, C3, true, backward);
+    addw(T_CONV4_K, TC_CONV4, 4, C3, C4, true, backward);
+    if (decoder) {
+        addw(T_DECONV1_K, TC_DECONV1, 4, C3, C4, backward, true);
+        addw(T_DECONV2_K, TC_DECONV2, 4, C2, C3, backward, true);
+        addw(T_DECONV3_K, TC_DECONV3, 5, C1, C2, backward, true);
+    }
+    return launch_tc_weights(params, pl.relayout, w, s);
 }
 
 static int32_t run_encoder(const VaePlan& pl, const VaeLayout& L, const cpb_vae_config* cfg, const float* params,
@@ -386,11 +465,14 @@ static int32_t run_encoder(const VaePlan& pl, const VaeLayout& L, const cpb_vae_
     TapGemmParams p = gather_problem(pl.xp, B, H0, W0, 4, 4, pl.relayout + pl.rl.conv1P, C1,
                                      params + L.off[T_CONV1_B], nullptr, pl.a1, 1);
     CPB_TRY(tg("conv1.fwd", p, s));
-    p = gather_problem(pl.a1, B, H1, W1, C1, 4, params + L.off[T_CONV2_K], C2, params + L.off[T_CONV2_B], nullptr, pl.a2, 1);
+    p = gather_problem(pl.a1, B, H1, W1, C1, 4, params + L.off[T_CONV2_K], C2, params + L.off[T_CONV2_B], nullptr, pl.a2, 1,
+                       pl.relayout + pl.rl.tc[TC_CONV2].f_hi, pl.relayout + pl.rl.tc[TC_CONV2].f_lo);
     CPB_TRY(tg("conv2.fwd", p, s));
-    p = gather_problem(pl.a2, B, H2, W2, C2, 4, params + L.off[T_CONV3_K], C3, params + L.off[T_CONV3_B], nullptr, pl.a3, 1);
+    p = gather_problem(pl.a2, B, H2, W2, C2, 4, params + L.off[T_CONV3_K], C3, params + L.off[T_CONV3_B], nullptr, pl.a3, 1,
+                       pl.relayout + pl.rl.tc[TC_CONV3].f_hi, pl.relayout + pl.rl.tc[TC_CONV3].f_lo);
     CPB_TRY(tg("conv3.fwd", p, s));
-    p = gather_problem(pl.a3, B, H3, W3, C3, 4, params + L.off[T_CONV4_K], C4, params + L.off[T_CONV4_B], nullptr, pl.a4, 1);
+    p = gather_problem(pl.a3, B, H3, W3, C3, 4, params + L.off[T_CONV4_K], C4, params + L.off[T_CONV4_B], nullptr, pl.a4, 1,
+                       pl.relayout + pl.rl.tc[TC_CONV4].f_hi, pl.relayout + pl.rl.tc[TC_CONV4].f_lo);
     CPB_TRY(tg("conv4.fwd", p, s));
     // both heads as one y-batched dense problem: heads[0] = mean, heads[1] = logstd_sq
     p = dense_problem(pl.a4, B, FEAT, params + L.off[T_MEAN_K], pl.z, params + L.off[T_MEAN_B], nullptr, pl.heads, 0);
@@ -410,14 +492,14 @@ static int32_t run_decoder(const VaePlan& pl, const VaeLayout& L, const float* p
                                     nullptr, pl.d1, 0);
     CPB_TRY(tg("dense1.fwd", p, s));
     p = scatter_problem(pl.d1, B, H4, W4, C4, 4, pl.relayout + pl.rl.deconv1T, C3, params + L.off[T_DECONV1_B],
-                        nullptr, pl.b1, H3, W3, 1);
-    CPB_TRY(tg("deconv1.fwd", p, s));
+                        nullptr, pl.b1, H3, W3, 1, pl.relayout + pl.rl.tc[TC_DECONV1].t_hi, pl.relayout + pl.rl.tc[TC_DECONV1].t_lo);
+    CPB_TRY(tg("deconv1.fwd", p, s, 4));
     p = scatter_problem(pl.b1, B, H3, W3, C3, 4, pl.relayout + pl.rl.deconv2T, C2, params + L.off[T_DECONV2_B],
-                        nullptr, pl.b2, H2, W2, 1);
-    CPB_TRY(tg("deconv2.fwd", p, s));
+                        nullptr, pl.b2, H2, W2, 1, pl.relayout + pl.rl.tc[TC_DECONV2].t_hi, pl.relayout + pl.rl.tc[TC_DECONV2].t_lo);
+    CPB_TRY(tg("deconv2.fwd", p, s, 4));
     p = scatter_problem(pl.b2, B, H2, W2, C2, 5, pl.relayout + pl.rl.deconv3T, C1, params + L.off[T_DECONV3_B],
-                        nullptr, pl.b3, H1, W1, 1);
-    CPB_TRY(tg("deconv3.fwd", p, s));
+                        nullptr, pl.b3, H1, W1, 1, pl.relayout + pl.rl.tc[TC_DECONV3].t_hi, pl.relayout + pl.rl.tc[TC_DECONV3].t_lo);
+    CPB_TRY(tg("deconv3.fwd", p, s, 5));
     ProfScope prof("deconv4.fwd", s);
     return launch_deconv4_fwd(pl.b3, params + L.off[T_DECONV4_K], params + L.off[T_DECONV4_B], B, pl.ct, logits_p,
                               sigm, s);
@@ -465,19 +547,22 @@ static int32_t run_backward(const VaePlan& pl, const VaeLayout& L, const cpb_vae
     CPB_TRY(run_wgrad("deconv3.wgrad", pl.gA, W1, C1, (long long)H1 * W1 * C1, 5, pl.b2, B, H2, W2, C2, 5 * 5 * C1, 5 * 5 * C1,
                       pl.partial, grads + L.off[T_DECONV3_K], s));
     CPB_TRY(launch_colsum(pl.gA, (long long)B * H1 * W1, C1, C1, grads + L.off[T_DECONV3_B], cs, s));
-    p = gather_problem(pl.gA, B, H1, W1, C1, 5, params + L.off[T_DECONV3_K], C2, nullptr, pl.b2, pl.gB, 0);
+    p = gather_problem(pl.gA, B, H1, W1, C1, 5, params + L.off[T_DECONV3_K], C2, nullptr, pl.b2, pl.gB, 0,
+                       pl.relayout + pl.rl.tc[TC_DECONV3].f_hi, pl.relayout + pl.rl.tc[TC_DECONV3].f_lo);
     CPB_TRY(tg("deconv3.dgrad", p, s));                                   // gB = g(b2)
     // ---- deconv2
     CPB_TRY(run_wgrad("deconv2.wgrad", pl.gB, W2, C2, (long long)H2 * W2 * C2, 4, pl.b1, B, H3, W3, C3, 16 * C2, 16 * C2, pl.partial,
                       grads + L.off[T_DECONV2_K], s));
     CPB_TRY(launch_colsum(pl.gB, (long long)B * H2 * W2, C2, C2, grads + L.off[T_DECONV2_B], cs, s));
-    p = gather_problem(pl.gB, B, H2, W2, C2, 4, params + L.off[T_DECONV2_K], C3, nullptr, pl.b1, pl.gA, 0);
+    p = gather_problem(pl.gB, B, H2, W2, C2, 4, params + L.off[T_DECONV2_K], C3, nullptr, pl.b1, pl.gA, 0,
+                       pl.relayout + pl.rl.tc[TC_DECONV2].f_hi, pl.relayout + pl.rl.tc[TC_DECONV2].f_lo);
     CPB_TRY(tg("deconv2.dgrad", p, s));                                   // gA = g(b1)
     // ---- deconv1
     CPB_TRY(run_wgrad("deconv1.wgrad", pl.gA, W3, C3, (long long)H3 * W3 * C3, 4, pl.d1, B, H4, W4, C4, 16 * C3, 16 * C3, pl.partial,
                       grads + L.off[T_DECONV1_K], s));
     CPB_TRY(launch_colsum(pl.gA, (long long)B * H3 * W3, C3, C3, grads + L.off[T_DECONV1_B], cs, s));
-    p = gather_problem(pl.gA, B, H3, W3, C3, 4, params + L.off[T_DECONV1_K], C4, nullptr, nullptr, pl.gB, 0);
+    p = gather_problem(pl.gA, B, H3, W3, C3, 4, params + L.off[T_DECONV1_K], C4, nullptr, nullptr, pl.gB, 0,
+                       pl.relayout + pl.rl.tc[TC_DECONV1].f_hi, pl.relayout + pl.rl.tc[TC_DECONV1].f_lo);
     CPB_TRY(tg("deconv1.dgrad", p, s));                                   // gB = g(d1) [B, 6144]
     // ---- dense1
     CPB_TRY(run_dense_wgrad("dense1.wgrad", pl.zbuf, z, pl.gB, B, FEAT, pl.partial, grads + L.off[T_DENSE1_K], s));
@@ -502,20 +587,23 @@ static int32_t run_backward(const VaePlan& pl, const VaeLayout& L, const cpb_vae
     CPB_TRY(run_wgrad("conv4.wgrad", pl.a3, W3, C3, (long long)H3 * W3 * C3, 4, pl.gA, B, H4, W4, C4, 16 * C3, 16 * C3, pl.partial,
                       grads + L.off[T_CONV4_K], s));
     CPB_TRY(launch_colsum(pl.gA, (long long)B * H4 * W4, C4, C4, grads + L.off[T_CONV4_B], cs, s));
-    p = scatter_problem(pl.gA, B, H4, W4, C4, 4, pl.relayout + pl.rl.conv4T, C3, nullptr, pl.a3, pl.gB, H3, W3, 0);
-    CPB_TRY(tg("conv4.dgrad", p, s));                                   // gB = g(a3)
+    p = scatter_problem(pl.gA, B, H4, W4, C4, 4, pl.relayout + pl.rl.conv4T, C3, nullptr, pl.a3, pl.gB, H3, W3, 0,
+                        pl.relayout + pl.rl.tc[TC_CONV4].t_hi, pl.relayout + pl.rl.tc[TC_CONV4].t_lo);
+    CPB_TRY(tg("conv4.dgrad", p, s, 4));                                   // gB = g(a3)
     // ---- conv3
     CPB_TRY(run_wgrad("conv3.wgrad", pl.a2, W2, C2, (long long)H2 * W2 * C2, 4, pl.gB, B, H3, W3, C3, 16 * C2, 16 * C2, pl.partial,
                       grads + L.off[T_CONV3_K], s));
     CPB_TRY(launch_colsum(pl.gB, (long long)B * H3 * W3, C3, C3, grads + L.off[T_CONV3_B], cs, s));
-    p = scatter_problem(pl.gB, B, H3, W3, C3, 4, pl.relayout + pl.rl.conv3T, C2, nullptr, pl.a2, pl.gA, H2, W2, 0);
-    CPB_TRY(tg("conv3.dgrad", p, s));                                   // gA = g(a2)
+    p = scatter_problem(pl.gB, B, H3, W3, C3, 4, pl.relayout + pl.rl.conv3T, C2, nullptr, pl.a2, pl.gA, H2, W2, 0,
+                        pl.relayout + pl.rl.tc[TC_CONV3].t_hi, pl.relayout + pl.rl.tc[TC_CONV3].t_lo);
+    CPB_TRY(tg("conv3.dgrad", p, s, 4));                                   // gA = g(a2)
     // ---- conv2
     CPB_TRY(run_wgrad("conv2.wgrad", pl.a1, W1, C1, (long long)H1 * W1 * C1, 4, pl.gA, B, H2, W2, C2, 16 * C1, 16 * C1, pl.partial,
                       grads + L.off[T_CONV2_K], s));
     CPB_TRY(launch_colsum(pl.gA, (long long)B * H2 * W2, C2, C2, grads + L.off[T_CONV2_B], cs, s));
-    p = scatter_problem(pl.gA, B, H2, W2, C2, 4, pl.relayout + pl.rl.conv2T, C1, nullptr, pl.a1, pl.gB, H1, W1, 0);
-    CPB_TRY(tg("conv2.dgrad", p, s));                                   // gB = g(a1)
+    p = scatter_problem(pl.gA, B, H2, W2, C2, 4, pl.relayout + pl.rl.conv2T, C1, nullptr, pl.a1, pl.gB, H1, W1, 0,
+                        pl.relayout + pl.rl.tc[TC_CONV2].t_hi, pl.relayout + pl.rl.tc[TC_CONV2].t_lo);
+    CPB_TRY(tg("conv2.dgrad", p, s, 4));                                   // gB = g(a1)
     // ---- conv1 (its input gradient is never used: the reference computes and discards it)
     CPB_TRY(run_wgrad("conv1.wgrad", pl.xp, W0, 4, (long long)NPIX * 4, 4, pl.gB, B, H1, W1, C1, 4, 3, pl.partial,
                       grads + L.off[T_CONV1_K], s));
@@ -533,9 +621,40 @@ using namespace cpb;
 extern "C" {
 
 const char* cpb_last_error(void) { return cpb::g_err; }
-const char* cpb_build_info(void) { return "carla_ppo_b200 0.1 (sm_100a, fp32 SIMT tap-GEMM)"; }
+const char* cpb_build_info(void) { return "carla_ppo_b200 0.2 (sm_100a; tcgen05 3xTF32 + fp32 SIMT tap-GEMM)"; }
 int64_t cpb_launch_count(void) { return cpb::g_launches; }
 void cpb_reset_launch_count(void) { cpb::g_launches = 0; }
+
+/* debug: byte offsets of the named workspace buffers for (batch, ct, z, mode); returns the count written */
+int32_t cpb_debug_vae_buffer_offsets(int32_t batch, int32_t ct, int32_t z, int32_t mode, int64_t* offsets, int32_t capacity) {
+    char* base = (char*)4096;   // fake non-null base: only differences are used
+    VaePlan pl = make_plan(base, (int64_t)1 << 60, batch, ct, z, mode);
+    const float* ptrs[] = {pl.xp, pl.a1, pl.a2, pl.a3, pl.a4, pl.heads, pl.zbuf, pl.d1, pl.b1, pl.b2, pl.b3, pl.logits_p, pl.gA, pl.gB};
+    const int n = (int)(sizeof(ptrs) / sizeof(ptrs[0]));
+    for (int i = 0; i < n && i < capacity; ++i) offsets[i] = ptrs[i] ? (int64_t)((const char*)ptrs[i] - base) : -1;
+    return n;
+}
+
+/* debug: D[M,N] = A[M,K] * Bt[N,K]^T through the tensor-core tap-GEMM (dense, one tap).  scratch: 2*N*K floats. */
+int32_t cpb_debug_tc_gemm(const float* a, const float* bt, float* d, int32_t m, int32_t n, int32_t k, float* scratch, void* stream) {
+    CPB_TRY(ensure_init());
+    cudaStream_t s = (cudaStream_t)stream;
+    TcWeightTable w;
+    memset(&w, 0, sizeof(w));
+    w.njobs = 1; w.total = (long long)n * k;
+    w.jobs[0].src_off = 0; w.jobs[0].dst_hi = 0; w.jobs[0].dst_lo = (long long)n * k; w.jobs[0].mode = 0; w.jobs[0].count = w.total;
+    CPB_TRY(launch_tc_weights(bt, scratch, w, s));
+    TapGemmParams p = dense_problem(a, m, k, nullptr, n, nullptr, nullptr, d, 0);
+    p.wk_hi = scratch; p.wk_lo = scratch + (long long)n * k;
+    return launch_tc_tapgemm(p, s);
+}
+
+int32_t cpb_set_math_mode(int32_t mode) {
+    CPB_REQUIRE(mode == 0 || mode == 1, "math mode must be 0 (fp32 SIMT) or 1 (3xTF32 tcgen05)");
+    cpb::g_math_mode = mode;
+    return CPB_OK;
+}
+int32_t cpb_get_math_mode(void) { return cpb::g_math_mode; }
 
 void cpb_profile_enable(int32_t on) { cpb::g_profile_on = on != 0; }
 void cpb_profile_reset(void) {

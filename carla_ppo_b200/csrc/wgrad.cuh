@@ -34,6 +34,12 @@ int wgrad_pick_splits(int I, int J, long long M);
 int32_t launch_wgrad(const WgradParams& p, cudaStream_t stream);
 int32_t wgrad_init();
 
+// tensor-core (tcgen05, 3xTF32) variant -- tc_wgrad.cu.  Same WgradParams; m_per_split must be a multiple of 32.
+int32_t tc_wgrad_init();
+bool tc_wgrad_supported(int I, int J, int run);
+int tc_wgrad_pick_splits(int I, int J, long long M);
+int32_t launch_tc_wgrad(const WgradParams& p, cudaStream_t stream);
+
 // out[(t*c_real + c)*J + j] = sum_s partial[s][(t*c_pad + c)][j]   for c < c_real
 int32_t launch_reduce_partials(const float* partial, int splits, int I, int J, int c_pad, int c_real,
                                float* out, cudaStream_t stream);

@@ -198,6 +198,20 @@ int32_t cpb_ppo_learn(const cpb_ppo_config* cfg, float* params, float* params_ol
                       const int32_t* perms, float* metrics, void* workspace,
                       int64_t workspace_bytes, void* stream);
 
+/* Arithmetic used for the dense conv / transposed-conv contractions of the VAE (both are fp32-accurate):
+ *   1 (default) tcgen05.mma kind::tf32 with the error-compensated 3xTF32 split, fp32 accumulators in TMEM;
+ *   0           fp32 FMA (SIMT) tap-GEMM -- also used in mode 1 for the layers the tensor-core kernel does
+ *               not cover (3-channel edge layers, dense heads, weight gradients). */
+int32_t cpb_set_math_mode(int32_t mode);
+/* Debug / test hooks (not part of the reference-facing surface): workspace buffer offsets in bytes for
+ * [xp,a1,a2,a3,a4,heads,z,d1,b1,b2,b3,logits_p,gA,gB] (-1 = absent in that mode), and a dense
+ * D[M,N] = A[M,K] * Bt[N,K]^T through the tensor-core kernel (scratch: 2*N*K floats). */
+int32_t cpb_debug_vae_buffer_offsets(int32_t batch, int32_t target_channels, int32_t z_dim, int32_t mode,
+                                     int64_t* offsets, int32_t capacity);
+int32_t cpb_debug_tc_gemm(const float* a, const float* bt, float* d, int32_t m, int32_t n, int32_t k,
+                          float* scratch, void* stream);
+int32_t cpb_get_math_mode(void);
+
 /* Counters for bench.py's `gpu_launches`: kernels launched by this library since the last reset. */
 int64_t cpb_launch_count(void);
 void    cpb_reset_launch_count(void);

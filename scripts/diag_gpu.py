@@ -10,6 +10,10 @@ from oracle import vae_oracle as vo, torch_ref as tr
 from carla_ppo_b200.vae.models import ConvVAE
 
 tmp = tempfile.mkdtemp()
+from carla_ppo_b200 import _lib
+MODE = int(os.environ.get("CPB_MATH_MODE", "1"))
+_lib.check(_lib.load().cpb_set_math_mode(MODE))
+print("math mode", _lib.load().cpb_get_math_mode())
 def make(w, **kw):
     v = ConvVAE((80,160,3), z_dim=64, loss_fn=kw.pop("loss","mse"), model_dir=tmp, seed=0, **kw); v.init_session(init_logging=False); v.set_weights(w); return v
 def dev(a): return torch.as_tensor(np.ascontiguousarray(a), device="cuda")
