@@ -3,13 +3,16 @@
 //   gw[i, j] = sum_{m}  big[row(m) + tap_off[i / run] + i % run] * small[m * J + j]        (same contract as wgrad.cu)
 //
 // as D[128 x BN] += A^T B with the REDUCTION index m on the MMA K axis.  Both operands are activations / gradients
-// (nothing can be pre-split), and in NHWC memory the channel index -- not m -- is contiguous, so the loader
-// transposes on the fly: lane = reduction position (32 per k-block), each thread reads float4s of 4 channels for
-// its position, splits them into TF32 hi / lo parts, and scatters 4-byte stores into the K-major SWIZZLE_128B
-// tiles (for a fixed channel row the 32 lanes fill one 128-byte row: conflict-free).  MMA issue, the 3xTF32
-// products, the separate cross-term tile and the chunked drain into fp32 register accumulators are those of
-// tc_tapgemm.cu.  Each (i-tile, j-tile, split) CTA writes its partial [128 x BN] block; reduce_partials() sums the
-// splits in a fixed order (deterministic).
+// (nothing can be pre-split), and in NHWC memory the channel index -- not m -- is contiguous, while the tensor
+// core wants K-major tiles (for 32-bit operands the MN-major alternative is the special SWIZZLE_128B_BASE32B
+// layout).  The loader therefore transposes 4x4 blocks in registers: a thread reads the float4 of 4 channels at
+// 4 consecutive reduction positions (4 x LDG.128), regroups them into 4 vectors "one channel x 4 positions",
+// splits them into TF32 hi / lo parts and writes each as ONE 16-byte chunk of the K-major SWIZZLE_128B tile
+// (8 STS.128).  Lanes of a quarter-warp own the same channel group and the 8 different position blocks, so the
+// swizzled chunk index (block ^ row%8) spreads them over all banks (conflict-free), and a warp's loads cover
+// 8 rows x 64 contiguous bytes.  MMA issue, the 3xTF32 products, the separate cross-term tile and the chunked
+// drain into fp32 register accumulators are those of tc_tapgemm.cu.  Each (i-tile, j-tile, split) CTA writes its
+// partial [128 x BN] block; reduce_partials() sums the splits in a fixed order (deterministic).
 #include "tc_common.cuh"
 #include "wgrad.cuh"
 
@@ -30,11 +33,6 @@ struct TcWgCfg {
     static constexpr int TMEM_COLS = BN == 128 ? 512 : (BN == 64 ? 256 : 128);
 };
 
-// byte offset of element (row, k) of a K-major SWIZZLE_128B tile (rows of 32 floats)
-__device__ __forceinline__ uint32_t sw_off(int row, int k) {
-    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 2) ^ (row & 7))) << 4) + (k & 3) * 4);
-}
-
 template <int BN>
 __global__ void __launch_bounds__(256, 1)
 tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
@@ -42,7 +40,6 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
     constexpr int STAGES = Cfg::STAGES;
     constexpr int B_TILE_BYTES = Cfg::B_TILE_BYTES;
     constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
-    constexpr int BG = BN / 32;                       // float4 column groups of B per warp
     static_assert(STAGES <= CHUNK_KB, "late drain relies on the stage ring being no deeper than a chunk");
 
     extern __shared__ uint8_t smem_raw[];
@@ -77,49 +74,56 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
 
-    // ---- loader columns of this thread (fixed): A rows (warp*16 + g*4 .. +3), B rows (warp*BN/8 + g*4 .. +3)
-    long long a_coloff[4];
-    bool a_col_ok[4];
+    // ---- loader: thread = (channel group cg = warp*4 + lane/8, position block mb = lane%8)
+    const int cg = warp * 4 + (lane >> 3);
+    const int mb = lane & 7;
+    const int a_i = i0 + cg * 4;
+    const bool a_col_ok = a_i < p.I;
+    long long a_coloff = 0;
+    if (a_col_ok) {
+        const int tap = a_i / p.run;
+        a_coloff = p.tap_off[tap] + (a_i - tap * p.run);
+    }
+    const bool b_col_ok = cg * 4 < BN;
+    // swizzled chunk address of (row r = cg*4 + c, 16-byte chunk mb): rows 4cg..4cg+3 share the 1 KB group
+    uint32_t soff[4];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        const int i = i0 + (warp * 4 + g) * 4;
-        a_col_ok[g] = i < p.I;
-        a_coloff[g] = 0;
-        if (a_col_ok[g]) {
-            const int tap = i / p.run;
-            a_coloff[g] = p.tap_off[tap] + (i - tap * p.run);
-        }
+    for (int c = 0; c < 4; ++c) {
+        const int r = cg * 4 + c;
+        soff[c] = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((mb ^ (r & 7)) << 4));
     }
 
-    float4 areg[4], breg[BG];
+    float4 areg[4], breg[4];
     auto load_regs = [&](int kb) {
-        const long long m = m_begin + (long long)kb * TBK + lane;
-        const bool v = m < m_end;
-        long long base = 0;
-        if (v) {
-            const int n = (int)(m / HoWo);
+        long long m = m_begin + (long long)kb * TBK + mb * 4;
+        int n = 0, oy = 0, ox = 0;
+        if (m < m_end) {
+            n = (int)(m / HoWo);
             const int rem = (int)(m - (long long)n * HoWo);
-            const int oy = rem / p.Wo;
-            const int ox = rem - oy * p.Wo;
-            base = (long long)n * p.big_img + ((long long)(oy * p.sstride) * p.Wb + ox * p.sstride) * p.big_pitch;
+            oy = rem / p.Wo;
+            ox = rem - oy * p.Wo;
         }
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-            areg[g] = (v && a_col_ok[g]) ? __ldg(reinterpret_cast<const float4*>(p.big + base + a_coloff[g])) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int g = 0; g < BG; ++g)
-            breg[g] = v ? __ldg(reinterpret_cast<const float4*>(p.small + m * p.J + j0 + (warp * BG + g) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < 4; ++j) {
+            const bool v = m + j < m_end;
+            const long long base = (long long)n * p.big_img + ((long long)(oy * p.sstride) * p.Wb + ox * p.sstride) * p.big_pitch;
+            areg[j] = (v && a_col_ok) ? __ldg(reinterpret_cast<const float4*>(p.big + base + a_coloff)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            breg[j] = (v && b_col_ok) ? __ldg(reinterpret_cast<const float4*>(p.small + (m + j) * p.J + j0 + cg * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (++ox == p.Wo) { ox = 0; if (++oy == p.Ho) { oy = 0; ++n; } }
+        }
     };
 
-    auto store4 = [&](uint32_t tile_hi, uint32_t tile_lo, int row0, const float4& x) {
-        const float xv[4] = {x.x, x.y, x.z, x.w};
+    // 4x4 register transpose + split + store: x[j] = 4 channels at position j  ->  one chunk per channel
+    auto store_t = [&](uint32_t tile_hi, uint32_t tile_lo, const float4* x) {
+        const float xs[4][4] = {{x[0].x, x[1].x, x[2].x, x[3].x}, {x[0].y, x[1].y, x[2].y, x[3].y},
+                                {x[0].z, x[1].z, x[2].z, x[3].z}, {x[0].w, x[1].w, x[2].w, x[3].w}};
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            float hi, lo;
-            split_tf32(xv[c], hi, lo);
-            const uint32_t o = sw_off(row0 + c, lane);
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(tile_hi + o), "f"(hi) : "memory");
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(tile_lo + o), "f"(lo) : "memory");
+            float4 hi, lo;
+            split_tf32(xs[c][0], hi.x, lo.x); split_tf32(xs[c][1], hi.y, lo.y);
+            split_tf32(xs[c][2], hi.z, lo.z); split_tf32(xs[c][3], hi.w, lo.w);
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(tile_hi + soff[c]), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(tile_lo + soff[c]), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
         }
     };
 
@@ -157,11 +161,8 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
         if (kb % CHUNK_KB == 0) {
             while (drained < kb / CHUNK_KB - 1) drain_one();
         }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) store4(stage, stage + A_TILE_BYTES, (warp * 4 + g) * 4, areg[g]);
-#pragma unroll
-        for (int g = 0; g < BG; ++g)
-            store4(stage + 2 * A_TILE_BYTES, stage + 2 * A_TILE_BYTES + B_TILE_BYTES, (warp * BG + g) * 4, breg[g]);
+        store_t(stage, stage + A_TILE_BYTES, areg);
+        if (b_col_ok) store_t(stage + 2 * A_TILE_BYTES, stage + 2 * A_TILE_BYTES + B_TILE_BYTES, breg);
         if (kb + 1 < nkb) load_regs(kb + 1);
 
         fence_async_smem();
@@ -178,10 +179,10 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
             const uint32_t d_cross = tmem_base + (uint32_t)(2 * BN);
 #pragma unroll
             for (int ks = 0; ks < TBK / 8; ++ks) {
-                const uint64_t adv = (uint64_t)(ks * 2);
-                umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, ((kb % CHUNK_KB) | ks) != 0 ? 1u : 0u);
-                umma_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
-                umma_tf32(d_cross, a_hi + adv, b_lo + adv, idesc, 1u);
+                const uint64_t adva = (uint64_t)(ks * 2), advb = adva;          // 32 bytes per k-step (K-major)
+                umma_tf32(d_main, a_hi + adva, b_hi + advb, idesc, ((kb % CHUNK_KB) | ks) != 0 ? 1u : 0u);
+                umma_tf32(d_cross, a_lo + adva, b_hi + advb, idesc, (kb | ks) != 0 ? 1u : 0u);
+                umma_tf32(d_cross, a_hi + adva, b_lo + advb, idesc, 1u);
             }
             umma_commit(&empty_bar[s]);
             if (kb % CHUNK_KB == CHUNK_KB - 1 || kb == nkb - 1) umma_commit(&chunk_bar[chunk & 1]);
@@ -245,7 +246,7 @@ bool tc_wgrad_supported(int I, int J, int run) { return run % 4 == 0 && J % 32 =
 
 int tc_wgrad_pick_splits(int I, int J, long long M) {
     const long long tiles = (long long)cdiv(I, TBM) * (J / tc_wg_bn(J));
-    long long splits = (148 + tiles - 1) / tiles;          // one CTA per SM (192 KB of shared memory each)
+    long long splits = 148 / tiles;                         // ONE wave: one CTA per SM (192 KB of shared memory each)
     const long long max_splits = (M + 1023) / 1024;         // keep >= 1024 reduction positions per split
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;

@@ -649,6 +649,22 @@ int32_t cpb_debug_tc_gemm(const float* a, const float* bt, float* d, int32_t m, 
     return launch_tc_tapgemm(p, s);
 }
 
+/* debug: out[I,J] = big[M,I]^T small[M,J] through the tensor-core wgrad kernel (1x1 "image", one tap). */
+int32_t cpb_debug_tc_wgrad(const float* big, const float* small, float* out, int32_t m, int32_t i, int32_t j,
+                           int32_t variant, float* partial, void* stream) {
+    CPB_TRY(ensure_init());
+    cudaStream_t s = (cudaStream_t)stream;
+    WgradParams w;
+    memset(&w, 0, sizeof(w));
+    w.big = big; w.small = small; w.partial = partial;
+    w.batch = m; w.Wb = 1; w.big_pitch = i; w.big_img = i; w.Ho = w.Wo = 1; w.sstride = 1;
+    w.ntaps = 1; w.run = i; w.tap_off[0] = 0; w.I = i; w.J = j; w.tc_variant = variant;
+    w.splits = 2;
+    w.m_per_split = align_up(((long long)m + 1) / 2, 32);
+    CPB_TRY(launch_tc_wgrad(w, s));
+    return launch_reduce_partials(partial, w.splits, i, j, i, i, out, s);
+}
+
 int32_t cpb_set_math_mode(int32_t mode) {
     CPB_REQUIRE(mode == 0 || mode == 1, "math mode must be 0 (fp32 SIMT) or 1 (3xTF32 tcgen05)");
     cpb::g_math_mode = mode;

@@ -208,6 +208,8 @@ int32_t cpb_set_math_mode(int32_t mode);
  * D[M,N] = A[M,K] * Bt[N,K]^T through the tensor-core kernel (scratch: 2*N*K floats). */
 int32_t cpb_debug_vae_buffer_offsets(int32_t batch, int32_t target_channels, int32_t z_dim, int32_t mode,
                                      int64_t* offsets, int32_t capacity);
+int32_t cpb_debug_tc_wgrad(const float* big, const float* small, float* out, int32_t m, int32_t i, int32_t j,
+                           int32_t variant, float* partial, void* stream);
 int32_t cpb_debug_tc_gemm(const float* a, const float* bt, float* d, int32_t m, int32_t n, int32_t k,
                           float* scratch, void* stream);
 int32_t cpb_get_math_mode(void);

@@ -143,9 +143,11 @@ def encode(params: Dict[str, np.ndarray], x: np.ndarray, keep=None):
     """vae/models.py:249-256 + :97-98.  Returns (mean, logstd_sq)."""
     a = x
     for name in ("conv1", "conv2", "conv3", "conv4"):
-        a = np.maximum(conv_gather(a, params["encoder/%s/kernel" % name]) + params["encoder/%s/bias" % name], 0.0)
+        pre = conv_gather(a, params["encoder/%s/kernel" % name]) + params["encoder/%s/bias" % name]
+        a = np.maximum(pre, 0.0)
         if keep is not None:
             keep[name] = a
+            keep["pre/" + name] = pre
     flat = a.reshape(a.shape[0], -1)            # tf.layers.flatten of NHWC -> (h, w, c) order
     mean = flat @ params["mean/kernel"] + params["mean/bias"]
     logvar = flat @ params["logstd_sqare/kernel"] + params["logstd_sqare/bias"]
@@ -159,9 +161,11 @@ def decode_logits(params: Dict[str, np.ndarray], z: np.ndarray, encoded_hw=(3, 8
     if keep is not None:
         keep["dense1"] = a
     for name in ("deconv1", "deconv2", "deconv3"):
-        a = np.maximum(conv_scatter(a, params["decoder/%s/kernel" % name]) + params["decoder/%s/bias" % name], 0.0)
+        pre = conv_scatter(a, params["decoder/%s/kernel" % name]) + params["decoder/%s/bias" % name]
+        a = np.maximum(pre, 0.0)
         if keep is not None:
             keep[name] = a
+            keep["pre/" + name] = pre
     logits = conv_scatter(a, params["decoder/deconv4/kernel"]) + params["decoder/deconv4/bias"]
     return logits
 
@@ -203,12 +207,19 @@ def verify_range(t):
 
 
 def loss_and_grads(params, x, y, eps, loss_type="mse", beta=1.0, kl_tolerance=0.0,
-                   want_grads=True, dtype=np.float64):
+                   want_grads=True, dtype=np.float64, relu_masks=None):
     """Forward + loss (+ reverse-mode gradients of ``loss = recon + beta*kl`` w.r.t. every variable).
 
     x [B,H,W,3], y [B,H,W,C_t] in [0,1]; eps [B,z] standard-normal draws (the TF Philox stream
     cannot be reproduced, so the noise is an input).  Returns a dict with mean, logvar, z, logits,
     recon, kl, loss and (if want_grads) grads{name: array}.
+
+    relu_masks (optional {layer: bool array}): ReLU activity pattern to use in the BACKWARD pass instead of
+    this run's own (pre > 0).  A finite-precision implementation and float64 disagree on the sign of the few
+    pre-activations that are ~0, and one such flip moves every downstream gradient by ~1/sqrt(#positions); the
+    GPU tests pass the device's own pattern here so that gradients are compared like for like, and check
+    separately that the two patterns differ only where |pre-activation| is negligible.  The dict returned also
+    carries "relu_pre" (float64 pre-activations) for that check.
     """
     p = {k: np.asarray(v, dtype) for k, v in params.items()}
     x = np.asarray(x, dtype); y = np.asarray(y, dtype); eps = np.asarray(eps, dtype)
@@ -232,9 +243,13 @@ def loss_and_grads(params, x, y, eps, loss_type="mse", beta=1.0, kl_tolerance=0.
         kl_active = kl_rows >= floor           # tf.maximum: gradient flows to kl_rows when it is the max
         kl_rows = np.maximum(kl_rows, floor)
     kl = kl_rows.mean()
-    out = dict(mean=mean, logvar=logvar, z=z, logits=logits, recon=recon, kl=kl, loss=recon + beta * kl)
+    out = dict(mean=mean, logvar=logvar, z=z, logits=logits, recon=recon, kl=kl, loss=recon + beta * kl,
+               relu_pre={k[4:]: v for k, v in keep.items() if k.startswith("pre/")})
     if not want_grads:
         return out
+    act = {}
+    for name in ("conv1", "conv2", "conv3", "conv4", "deconv1", "deconv2", "deconv3"):
+        act[name] = (keep[name] > 0) if relu_masks is None else np.asarray(relu_masks[name], bool).reshape(keep[name].shape)
 
     g = {}
     # ---- decoder backward
@@ -242,14 +257,14 @@ def loss_and_grads(params, x, y, eps, loss_type="mse", beta=1.0, kl_tolerance=0.
     w = p["decoder/deconv4/kernel"]
     g["decoder/deconv4/kernel"] = conv_wgrad(glog, keep["deconv3"], w.shape[0])
     g["decoder/deconv4/bias"] = glog.sum(axis=(0, 1, 2))
-    ga = conv_gather(glog, w) * (keep["deconv3"] > 0)
+    ga = conv_gather(glog, w) * act["deconv3"]
     for name, below in (("deconv3", "deconv2"), ("deconv2", "deconv1"), ("deconv1", "dense1")):
         w = p["decoder/%s/kernel" % name]
         g["decoder/%s/kernel" % name] = conv_wgrad(ga, keep[below], w.shape[0])
         g["decoder/%s/bias" % name] = ga.sum(axis=(0, 1, 2))
         ga = conv_gather(ga, w)
         if below != "dense1":
-            ga = ga * (keep[below] > 0)
+            ga = ga * act[below]
     gd = ga.reshape(bsz, -1)
     g["decoder/dense1/kernel"] = z.T @ gd
     g["decoder/dense1/bias"] = gd.sum(axis=0)
@@ -264,7 +279,7 @@ def loss_and_grads(params, x, y, eps, loss_type="mse", beta=1.0, kl_tolerance=0.
     g["logstd_sqare/kernel"] = flat.T @ glogvar
     g["logstd_sqare/bias"] = glogvar.sum(axis=0)
     gflat = gmean @ p["mean/kernel"].T + glogvar @ p["logstd_sqare/kernel"].T
-    ga = gflat.reshape(keep["conv4"].shape) * (keep["conv4"] > 0)
+    ga = gflat.reshape(keep["conv4"].shape) * act["conv4"]
     # ---- encoder backward
     inputs = {"conv4": keep["conv3"], "conv3": keep["conv2"], "conv2": keep["conv1"], "conv1": x}
     for name in ("conv4", "conv3", "conv2", "conv1"):
@@ -273,7 +288,7 @@ def loss_and_grads(params, x, y, eps, loss_type="mse", beta=1.0, kl_tolerance=0.
         g["encoder/%s/kernel" % name] = conv_wgrad(src, ga, w.shape[0])
         g["encoder/%s/bias" % name] = ga.sum(axis=(0, 1, 2))
         if name != "conv1":      # the reference computes conv1's input gradient too, and discards it
-            ga = conv_scatter(ga, w, out_hw=src.shape[1:3]) * (src > 0)
+            ga = conv_scatter(ga, w, out_hw=src.shape[1:3]) * act[{"conv4": "conv3", "conv3": "conv2", "conv2": "conv1"}[name]]
     out["grads"] = g
     return out
 
