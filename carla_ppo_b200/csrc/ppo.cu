@@ -43,7 +43,7 @@ PpoLayout make_ppo_layout(const cpb_ppo_config* c) {
 // small tile GEMM: C[M,N] (+)= A'[M,K] * B'[K,N], 32x32 tile, 64 threads, 4x4 per thread
 // ---------------------------------------------------------------------------------------------
 constexpr int TS = 32;   // tile edge
-constexpr int TK = 16;   // reduction chunk
+constexpr int TK = 32;   // reduction chunk (one global round trip per chunk: keep the chunk count low)
 
 // operand access descriptors (element (o, r) = output index o, reduction index r)
 struct Operand {
@@ -53,13 +53,14 @@ struct Operand {
     int gather_on_o;        // 1: gather indexes o, 0: gather indexes r
 };
 
-__device__ __forceinline__ float fetch(const Operand& a, int o, int r) {
-    long long oo = o, rr = r;
-    if (a.gather != nullptr) {
-        if (a.gather_on_o) oo = a.gather[o];
-        else rr = a.gather[r];
-    }
-    return a.p[oo * a.so + rr * a.sr];
+// GATHER: 0 = none, 1 = the A operand's output index goes through `gather`, 2 = its reduction index does.
+// Compile-time so that the 16 loads of a chunk stay independent (a run-time check serialised them: each
+// value load waited on a predicated index load that reused the same register).
+template <int GATHER>
+__device__ __forceinline__ long long a_offset(const Operand& a, int o, int r) {
+    if (GATHER == 1) return (long long)__ldg(a.gather + o) * a.so + (long long)r * a.sr;
+    if (GATHER == 2) return (long long)o * a.so + (long long)__ldg(a.gather + r) * a.sr;
+    return (long long)o * a.so + (long long)r * a.sr;
 }
 
 struct GemmJob {
@@ -77,13 +78,15 @@ struct GemmBatch {
     GemmJob job[2];
 };
 
+template <int GATHER>
 __global__ void __launch_bounds__(64)
 small_gemm_kernel(const __grid_constant__ GemmBatch batch) {
     const GemmJob& J = batch.job[blockIdx.z];
     const int m0 = blockIdx.x * TS, n0 = blockIdx.y * TS;
     if (m0 >= J.M || n0 >= J.N) return;
-    __shared__ __align__(16) float As[TK][TS + 4];
-    __shared__ __align__(16) float Bs[TK][TS + 4];
+    // double-buffered tiles: the global loads of chunk i+1 are in flight (in registers) while chunk i is multiplied
+    __shared__ __align__(16) float As[2][TK][TS + 4];
+    __shared__ __align__(16) float Bs[2][TK][TS + 4];
     const int tid = threadIdx.x;
     const int tx = tid & 7, ty = tid >> 3;      // 8 x 8 threads, 4x4 outputs each
     float acc[4][4];
@@ -93,24 +96,40 @@ small_gemm_kernel(const __grid_constant__ GemmBatch batch) {
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     float csum = 0.f;                            // column-sum lane (threads 0..31 own column n0+tid)
     const bool do_colsum = J.colsum != nullptr && blockIdx.x == 0;
+    const bool a_ofast = J.a.so <= J.a.sr, b_ofast = J.b.so <= J.b.sr;
 
-    for (int r0 = 0; r0 < J.R; r0 += TK) {
-        // 512 elements per operand, 8 per thread.  The faster-varying thread index follows the
-        // contiguous memory direction of each operand.
+    constexpr int EPT = TS * TK / 64;           // elements per thread per operand and chunk
+    float ra[EPT], rb[EPT];
+    auto fetch_chunk = [&](int r0) {
+        // TS*TK elements per operand; the faster-varying thread index follows the contiguous memory direction
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
+        for (int e = 0; e < EPT; ++e) {
             const int f = tid + e * 64;
             int o, r;
-            if (J.a.so <= J.a.sr) { o = f & 31; r = f >> 5; } else { r = f & 15; o = f >> 4; }
-            As[r][o] = (m0 + o < J.M && r0 + r < J.R) ? fetch(J.a, m0 + o, r0 + r) : 0.f;
-            if (J.b.so <= J.b.sr) { o = f & 31; r = f >> 5; } else { r = f & 15; o = f >> 4; }
-            Bs[r][o] = (n0 + o < J.N && r0 + r < J.R) ? fetch(J.b, n0 + o, r0 + r) : 0.f;
+            if (a_ofast) { o = f & 31; r = f >> 5; } else { r = f & (TK - 1); o = f / TK; }
+            ra[e] = (m0 + o < J.M && r0 + r < J.R) ? __ldg(J.a.p + a_offset<GATHER>(J.a, m0 + o, r0 + r)) : 0.f;
+            if (b_ofast) { o = f & 31; r = f >> 5; } else { r = f & (TK - 1); o = f / TK; }
+            rb[e] = (n0 + o < J.N && r0 + r < J.R) ? __ldg(J.b.p + (long long)(n0 + o) * J.b.so + (long long)(r0 + r) * J.b.sr) : 0.f;
+        }
+    };
+    fetch_chunk(0);
+    int buf = 0;
+    for (int r0 = 0; r0 < J.R; r0 += TK, buf ^= 1) {
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const int f = tid + e * 64;
+            int o, r;
+            if (a_ofast) { o = f & 31; r = f >> 5; } else { r = f & (TK - 1); o = f / TK; }
+            As[buf][r][o] = ra[e];
+            if (b_ofast) { o = f & 31; r = f >> 5; } else { r = f & (TK - 1); o = f / TK; }
+            Bs[buf][r][o] = rb[e];
         }
         __syncthreads();
+        if (r0 + TK < J.R) fetch_chunk(r0 + TK);
 #pragma unroll
         for (int k = 0; k < TK; ++k) {
-            const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-            const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
             const float av[4] = {a.x, a.y, a.z, a.w};
             const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
@@ -120,9 +139,8 @@ small_gemm_kernel(const __grid_constant__ GemmBatch batch) {
         }
         if (do_colsum && tid < 32) {
 #pragma unroll
-            for (int k = 0; k < TK; ++k) csum += Bs[k][tid];
+            for (int k = 0; k < TK; ++k) csum += Bs[buf][k][tid];
         }
-        __syncthreads();
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -149,7 +167,10 @@ int32_t launch_small_gemm(const GemmBatch& b, int njobs, cudaStream_t s) {
     }
     if (maxM == 0 || maxN == 0) return CPB_OK;
     dim3 grid(cdiv(maxM, TS), cdiv(maxN, TS), njobs);
-    small_gemm_kernel<<<grid, 64, 0, s>>>(b);
+    const int gather = b.job[0].a.gather == nullptr ? 0 : (b.job[0].a.gather_on_o ? 1 : 2);   // same for all jobs of a batch
+    if (gather == 0) small_gemm_kernel<0><<<grid, 64, 0, s>>>(b);
+    else if (gather == 1) small_gemm_kernel<1><<<grid, 64, 0, s>>>(b);
+    else small_gemm_kernel<2><<<grid, 64, 0, s>>>(b);
     CPB_LAUNCHED();
     return CPB_OK;
 }

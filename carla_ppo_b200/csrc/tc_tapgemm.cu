@@ -41,8 +41,11 @@ struct TcCfg {
 };
 constexpr int CHUNK_KB = 4;   // k-blocks accumulated inside TMEM before draining to registers (must be >= STAGES)
 
+constexpr int kLoaderThreads = 256;   // warps 0-7: loaders, accumulator drain, epilogue
+constexpr int kTcThreads = 288;       // + warp 8: MMA issuer (one elected lane)
+
 template <int BN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kTcThreads, 1)
 tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
     using Cfg = TcCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
@@ -50,32 +53,32 @@ tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
     constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
     constexpr int B_CHUNKS = BN * 8;                 // 16-byte chunks per B tile
     constexpr int B_ITERS = (B_CHUNKS + 255) / 256;
+    static_assert(STAGES <= CHUNK_KB, "late drain relies on the stage ring being no deeper than a chunk");
 
     extern __shared__ uint8_t smem_raw[];
-    static_assert(STAGES <= CHUNK_KB, "late drain relies on the stage ring being no deeper than a chunk");
-    __shared__ uint64_t empty_bar[STAGES];
-    __shared__ uint64_t chunk_bar[2];
+    __shared__ uint64_t full_bar[STAGES];     // loaders -> issuer: stage holds A(hi,lo) and B(hi,lo) of a k-block
+    __shared__ uint64_t empty_bar[STAGES];    // tensor core -> loaders: the MMAs reading the stage retired
+    __shared__ uint64_t chunk_bar[2];         // tensor core -> loaders: main tile b holds a finished 128-k chunk
+    __shared__ uint64_t drained_bar[2];       // loaders -> issuer: main tile b was added to the register accumulators
     __shared__ uint64_t done_bar;
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int cls_id = blockIdx.z;
-    const TapClass& cls = p.cls[cls_id];
+    const TapClass& cls = p.cls[blockIdx.z];
     const int Wo = cls.Wo;
     const int HoWo = cls.Ho * Wo;
     const long long M = (long long)p.batch * HoWo;
     const long long m0 = (long long)blockIdx.x * TBM;
     if (m0 >= M) return;                              // uniform per CTA: safe before any barrier / alloc
     const int n0 = blockIdx.y * BN;
-
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) mbar_init(&empty_bar[s], 1);
-        mbar_init(&chunk_bar[0], 1);
-        mbar_init(&chunk_bar[1], 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], kLoaderThreads); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&chunk_bar[0], 1); mbar_init(&chunk_bar[1], 1);
+        mbar_init(&drained_bar[0], kLoaderThreads); mbar_init(&drained_bar[1], kLoaderThreads);
         mbar_init(&done_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -85,84 +88,78 @@ tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
 
-    // ---- per-thread A-loader rows: 8 threads cover the 128 bytes of one row, 32 rows per pass, 4 passes
-    const int a_chunk = tid & 7;
-    long long a_base[4];
-    int a_iy[4], a_ix[4];
-    bool a_ok[4];
-    uint32_t a_soff[4];
+    const int nkb = cls.ntaps * (p.C / TBK);
+    const int nchunks = (nkb + CHUNK_KB - 1) / CHUNK_KB;
+
+    if (warp == 8) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+            const uint32_t d_cross = tmem_base + (uint32_t)(2 * BN);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t stage = smem_base + s * STAGE_BYTES;
+                const int chunk = kb / CHUNK_KB;
+                mbar_wait(&full_bar[s], (uint32_t)((kb / STAGES) & 1));
+                if (kb % CHUNK_KB == 0 && chunk >= 2)      // main tile (chunk & 1) must have been drained (chunk - 2)
+                    mbar_wait(&drained_bar[chunk & 1], (uint32_t)(((chunk >> 1) - 1) & 1));
+                tc_fence_after();
+                const uint64_t a_hi = make_desc(stage);
+                const uint64_t a_lo = make_desc(stage + A_TILE_BYTES);
+                const uint64_t b_hi = make_desc(stage + 2 * A_TILE_BYTES);
+                const uint64_t b_lo = make_desc(stage + 2 * A_TILE_BYTES + B_TILE_BYTES);
+                const uint32_t d_main = tmem_base + (uint32_t)((chunk & 1) * BN);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int r = (tid >> 3) + i * 32;
-        const long long m = m0 + r;
-        a_ok[i] = m < M;
-        const long long mm = a_ok[i] ? m : 0;
-        const int n = (int)(mm / HoWo);
-        const int rem = (int)(mm - (long long)n * HoWo);
-        const int oy = rem / Wo;
-        const int ox = rem - oy * Wo;
-        a_iy[i] = oy * p.sstride;
-        a_ix[i] = ox * p.sstride;
-        a_base[i] = (long long)n * p.src_img + ((long long)a_iy[i] * p.Ws + a_ix[i]) * p.src_pitch + a_chunk * 4;
-        a_soff[i] = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((a_chunk ^ (r & 7)) << 4));
-    }
-
-    const int cpb = p.C / TBK;
-    const int nkb = cls.ntaps * cpb;
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
-
-    auto load_a = [&](int tap_idx, int c0, float4* regs) {
-        const Tap& t = cls.taps[tap_idx];
+                for (int ks = 0; ks < TBK / 8; ++ks) {
+                    const uint64_t adv = (uint64_t)(ks * 2);      // 32 bytes per k-step, in 16-byte units
+                    umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, ((kb % CHUNK_KB) | ks) != 0 ? 1u : 0u);
+                    umma_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
+                    umma_tf32(d_cross, a_hi + adv, b_lo + adv, idesc, 1u);
+                }
+                umma_commit(&empty_bar[s]);
+                if (kb % CHUNK_KB == CHUNK_KB - 1 || kb == nkb - 1) umma_commit(&chunk_bar[chunk & 1]);
+                if (kb == nkb - 1) umma_commit(&done_bar);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================================ loaders / drain / epilogue ================================
+        // A rows: 8 threads cover the 128 bytes of one row, 32 rows per pass, 4 passes
+        const int a_chunk = tid & 7;
+        long long a_base[4];
+        int a_iy[4], a_ix[4];
+        bool a_ok[4];
+        uint32_t a_soff[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            bool v = a_ok[i];
-            if (p.check) v = v && (unsigned)(a_iy[i] + t.dy) < (unsigned)p.Hs && (unsigned)(a_ix[i] + t.dx) < (unsigned)p.Ws;
-            regs[i] = v ? __ldg(reinterpret_cast<const float4*>(p.src + a_base[i] + t.src_off + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int r = (tid >> 3) + i * 32;
+            const long long m = m0 + r;
+            a_ok[i] = m < M;
+            const long long mm = a_ok[i] ? m : 0;
+            const int n = (int)(mm / HoWo);
+            const int rem = (int)(mm - (long long)n * HoWo);
+            const int oy = rem / Wo;
+            const int ox = rem - oy * Wo;
+            a_iy[i] = oy * p.sstride;
+            a_ix[i] = ox * p.sstride;
+            a_base[i] = (long long)n * p.src_img + ((long long)a_iy[i] * p.Ws + a_ix[i]) * p.src_pitch + a_chunk * 4;
+            a_soff[i] = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((a_chunk ^ (r & 7)) << 4));
         }
-    };
-
-    // ---- register accumulators: this thread owns row (q*32 + lane) x columns [half*BN/2, +BN/2)
-    constexpr int HALF_COLS = BN / 2;
-    const int q = warp & 3;                      // TMEM lane quarter this warp may access
-    const int half = warp >> 2;                  // column half handled by this warp
-    const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * HALF_COLS);
-    float acc[HALF_COLS];
+        auto load_a = [&](int tap_idx, int c0, float4* regs) {
+            const Tap& t = cls.taps[tap_idx];
 #pragma unroll
-    for (int i = 0; i < HALF_COLS; ++i) acc[i] = 0.f;
-    const int nchunks = (nkb + CHUNK_KB - 1) / CHUNK_KB;
-    int drained = 0;
-    auto drain_one = [&]() {
-        const int b = drained & 1;
-        mbar_wait(&chunk_bar[b], (uint32_t)((drained >> 1) & 1));
-        tc_fence_after();
-#pragma unroll
-        for (int cc = 0; cc < HALF_COLS; cc += 16) {
-            float v[16];
-            tmem_ld16(tmem_lane + (uint32_t)(b * BN + cc), v);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) acc[cc + i] += v[i];
-        }
-        tc_fence_before();
-        ++drained;
-    };
-
-    float4 areg[4];
-    int ld_tap = 0, ld_c = 0;
-    load_a(0, 0, areg);
-
-    for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t stage = smem_base + s * STAGE_BYTES;
-        if (kb >= STAGES) mbar_wait(&empty_bar[s], (uint32_t)((kb / STAGES - 1) & 1));
-        if (kb % CHUNK_KB == 0) {
-            // chunk j = kb / CHUNK_KB is about to overwrite main tile (j & 1): chunks 0..j-2 must be in registers
-            while (drained < kb / CHUNK_KB - 1) drain_one();
-        }
-
-        // ---- B tiles (pre-split K-major weights): cp.async straight into the swizzled layout
-        {
-            const Tap& t = cls.taps[ld_tap];
-            const long long woff = t.w_off + (long long)n0 * p.C + ld_c;
+            for (int i = 0; i < 4; ++i) {
+                bool v = a_ok[i];
+                if (p.check) v = v && (unsigned)(a_iy[i] + t.dy) < (unsigned)p.Hs && (unsigned)(a_ix[i] + t.dx) < (unsigned)p.Ws;
+                regs[i] = v ? __ldg(reinterpret_cast<const float4*>(p.src + a_base[i] + t.src_off + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        // B tiles (pre-split K-major weights): cp.async straight into the swizzled layout, one k-block ahead of A
+        int b_tap = 0, b_c = 0;
+        auto issue_b = [&](int kbt) {
+            const uint32_t stage = smem_base + (kbt % STAGES) * STAGE_BYTES;
+            const Tap& t = cls.taps[b_tap];
+            const long long woff = t.w_off + (long long)n0 * p.C + b_c;
 #pragma unroll
             for (int it = 0; it < B_ITERS; ++it) {
                 const int f = tid + it * 256;
@@ -174,64 +171,86 @@ tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage + 2 * A_TILE_BYTES + B_TILE_BYTES + so), "l"(p.wk_lo + go));
                 }
             }
-            cp_async_commit();
-        }
-        // ---- A tile: split the prefetched fp32 rows into hi / lo and store both (swizzled)
+            b_c += TBK;
+            if (b_c == p.C) { b_c = 0; ++b_tap; }
+        };
+
+        // register accumulators: this thread owns row (q*32 + lane) x columns [half*BN/2, +BN/2)
+        constexpr int HALF_COLS = BN / 2;
+        const int q = warp & 3;                      // TMEM lane quarter this warp may access
+        const int half = warp >> 2;                  // column half handled by this warp
+        const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * HALF_COLS);
+        float acc[HALF_COLS];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float4 x = areg[i];
-            float4 hi, lo;
-            hi.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); lo.x = x.x - hi.x;
-            hi.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); lo.y = x.y - hi.y;
-            hi.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); lo.z = x.z - hi.z;
-            hi.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); lo.w = x.w - hi.w;
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage + a_soff[i]), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage + A_TILE_BYTES + a_soff[i]), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
-        }
-        // ---- prefetch the next k-block's A rows (latency overlaps the barrier + the MMAs in flight)
-        ld_c += TBK;
-        if (ld_c == p.C) { ld_c = 0; ++ld_tap; }
-        if (kb + 1 < nkb) load_a(ld_tap, ld_c, areg);
-
-        cp_async_wait<0>();
-        fence_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        __syncthreads();
-
-        if (tid == 0) {
+        for (int i = 0; i < HALF_COLS; ++i) acc[i] = 0.f;
+        int drained = 0;
+        auto drain_one = [&]() {
+            const int b = drained & 1;
+            mbar_wait(&chunk_bar[b], (uint32_t)((drained >> 1) & 1));
             tc_fence_after();
-            const uint64_t a_hi = make_desc(stage);
-            const uint64_t a_lo = make_desc(stage + A_TILE_BYTES);
-            const uint64_t b_hi = make_desc(stage + 2 * A_TILE_BYTES);
-            const uint64_t b_lo = make_desc(stage + 2 * A_TILE_BYTES + B_TILE_BYTES);
-            const int chunk = kb / CHUNK_KB;
-            const uint32_t d_main = tmem_base + (uint32_t)((chunk & 1) * BN);
-            const uint32_t d_cross = tmem_base + (uint32_t)(2 * BN);
 #pragma unroll
-            for (int ks = 0; ks < TBK / 8; ++ks) {
-                const uint64_t adv = (uint64_t)(ks * 2);      // 32 bytes per k-step, in 16-byte units
-                umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, ((kb % CHUNK_KB) | ks) != 0 ? 1u : 0u);
-                umma_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
-                umma_tf32(d_cross, a_hi + adv, b_lo + adv, idesc, 1u);
+            for (int cc = 0; cc < HALF_COLS; cc += 16) {
+                float v[16];
+                tmem_ld16(tmem_lane + (uint32_t)(b * BN + cc), v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[cc + i] += v[i];
             }
-            umma_commit(&empty_bar[s]);
-            if (kb % CHUNK_KB == CHUNK_KB - 1 || kb == nkb - 1) umma_commit(&chunk_bar[chunk & 1]);
-            if (kb == nkb - 1) umma_commit(&done_bar);
-        }
-    }
+            tc_fence_before();
+            mbar_arrive(&drained_bar[b]);
+            ++drained;
+        };
 
-    // ---- drain what is still in TMEM (last one or two chunks, then the cross-term tile)
-    while (drained < nchunks) drain_one();
-    mbar_wait(&done_bar, 0);
-    tc_fence_after();
+        float4 areg[4];
+        int ld_tap = 0, ld_c = 0;
+        load_a(0, 0, areg);
+        issue_b(0);
+        cp_async_commit();
+
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t stage = smem_base + s * STAGE_BYTES;
+            // B(kb+1) into the next stage (free once the MMAs of k-block kb+1-STAGES retired); stage s itself was
+            // claimed the same way one iteration ago.
+            if (kb + 1 < nkb) {
+                if (kb + 1 >= STAGES) mbar_wait(&empty_bar[(kb + 1) % STAGES], (uint32_t)(((kb + 1) / STAGES - 1) & 1));
+                issue_b(kb + 1);
+            }
+            cp_async_commit();
+            // late drain: chunk j-2 retired long ago (the stage ring is no deeper than a chunk), never blocks
+            if (kb % CHUNK_KB == 0) {
+                while (drained < kb / CHUNK_KB - 1) drain_one();
+            }
+            // A tile: split the prefetched fp32 rows into hi / lo and store both (swizzled)
 #pragma unroll
-    for (int cc = 0; cc < HALF_COLS; cc += 16) {
-        float v[16];
-        tmem_ld16(tmem_lane + (uint32_t)(2 * BN + cc), v);
+            for (int i = 0; i < 4; ++i) {
+                const float4 x = areg[i];
+                float4 hi, lo;
+                split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y); split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage + a_soff[i]), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage + A_TILE_BYTES + a_soff[i]), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+            }
+            // prefetch the next k-block's A rows
+            ld_c += TBK;
+            if (ld_c == p.C) { ld_c = 0; ++ld_tap; }
+            if (kb + 1 < nkb) load_a(ld_tap, ld_c, areg);
+
+            cp_async_wait<1>();          // everything but the group just committed: this thread's B(kb) chunks landed
+            fence_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            mbar_arrive(&full_bar[s]);
+        }
+
+        // drain what is still in TMEM (last one or two chunks, then the cross-term tile)
+        while (drained < nchunks) drain_one();
+        mbar_wait(&done_bar, 0);
+        tc_fence_after();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) acc[cc + i] += v[i];
-    }
-    // ---- epilogue from registers: bias / ReLU / mask -> global
-    {
+        for (int cc = 0; cc < HALF_COLS; cc += 16) {
+            float v[16];
+            tmem_ld16(tmem_lane + (uint32_t)(2 * BN + cc), v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[cc + i] += v[i];
+        }
+        // epilogue from registers: bias / ReLU / mask -> global
         const int row = q * 32 + lane;
         const long long m = m0 + row;
         if (m < M) {
@@ -287,7 +306,7 @@ int32_t tc_launch(const TapGemmParams& p, cudaStream_t stream) {
     }
     if (max_m == 0) return CPB_OK;
     dim3 grid((unsigned)((max_m + TBM - 1) / TBM), (unsigned)(p.N / BN), (unsigned)p.nclass);
-    tc_tapgemm_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(p);
+    tc_tapgemm_kernel<BN><<<grid, kTcThreads, Cfg::SMEM_BYTES, stream>>>(p);
     CPB_LAUNCHED();
     return CPB_OK;
 }

@@ -8,9 +8,9 @@
 // layout).  The loader therefore transposes 4x4 blocks in registers: a thread reads the float4 of 4 channels at
 // 4 consecutive reduction positions (4 x LDG.128), regroups them into 4 vectors "one channel x 4 positions",
 // splits them into TF32 hi / lo parts and writes each as ONE 16-byte chunk of the K-major SWIZZLE_128B tile
-// (8 STS.128).  Lanes of a quarter-warp own the same channel group and the 8 different position blocks, so the
-// swizzled chunk index (block ^ row%8) spreads them over all banks (conflict-free), and a warp's loads cover
-// 8 rows x 64 contiguous bytes.  MMA issue, the 3xTF32 products, the separate cross-term tile and the chunked
+// (8 STS.128).  Lanes of a quarter-warp own 2 adjacent channel groups x 4 position blocks, so the swizzled chunk
+// index (block ^ row%8) spreads them over all banks (conflict-free), and a warp's loads cover 4 rows x 128
+// contiguous bytes (fully coalesced).  MMA issue, the 3xTF32 products, the separate cross-term tile and the chunked
 // drain into fp32 register accumulators are those of tc_tapgemm.cu.  Each (i-tile, j-tile, split) CTA writes its
 // partial [128 x BN] block; reduce_partials() sums the splits in a fixed order (deterministic).
 #include "tc_common.cuh"
@@ -74,9 +74,12 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
 
-    // ---- loader: thread = (channel group cg = warp*4 + lane/8, position block mb = lane%8)
-    const int cg = warp * 4 + (lane >> 3);
-    const int mb = lane & 7;
+    // ---- loader: thread = (channel group cg of 4 channels, position block mb of 4 reduction positions).
+    //      A quarter-warp holds 2 adjacent channel groups x 4 position blocks: its 8 swizzled chunk slots
+    //      (mb ^ row%8, rows r and r+4) are distinct -> conflict-free STS.128; a warp's LDG.128 covers 4 rows x
+    //      128 contiguous bytes (8 channel groups) -> fully coalesced.
+    const int cg = (warp >> 1) * 8 + ((lane >> 3) & 3) * 2 + ((lane >> 2) & 1);
+    const int mb = (warp & 1) * 4 + (lane & 3);
     const int a_i = i0 + cg * 4;
     const bool a_col_ok = a_i < p.I;
     long long a_coloff = 0;
