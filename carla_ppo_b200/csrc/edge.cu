@@ -1,0 +1,214 @@
+// The two 3-channel "edge" layers of the ConvVAE (conv1: 80x160x3 -> 39x79x32, and deconv4's gradient side).
+// Their contraction is short (K = 4*4*Cb = 48, N = 32): the generic tap-GEMM spends its time in pipeline
+// prologues, and per frame they only move ~360 KB -- they should run near the HBM roofline.  Dedicated kernels:
+//
+//   edge_gather_kernel : small[b,i,j,0:32] = epi( sum_{kh,kw,c<CB} big4[b,2i+kh,2j+kw,c] * W[kh,kw,c,0:32] )
+//                        big4 is the float4-per-pixel padded image (prep_frames / recon_loss write it).
+//                        conv1 forward (epi = bias+ReLU) and conv2d_transpose(deconv4) data-gradient (epi = ReLU mask).
+//                        One thread = 2 horizontally adjacent output pixels x 32 channels: every weight float4 read
+//                        from shared memory (warp-broadcast) feeds 8 FMAs, the padded channel is skipped.
+//   edge_wgrad_kernel  : gw[kh,kw,c,j] = sum_{b,i,j'} big4[b,2i+kh,2j'+kw,c] * small[b,i,j',j]   (Conv2DBackpropFilter)
+//                        One CTA walks output rows; per row it stages the 4 big rows and the small row in shared
+//                        memory (cp.async), each warp accumulates the FULL [16*CB x 32] tile over its share of the
+//                        row's positions with a 12x4 (or 4x4 when CB=1) register micro-tile, warps are combined
+//                        through shared memory and each CTA writes one partial; reduce_partials sums them.
+#include "elementwise.cuh"
+
+namespace cpb {
+
+namespace {
+
+constexpr int EH = 80, EW = 160, SH = 39, SW = 79, SC = 32;   // big image (pixels), small image, small channels
+
+template <int CB, int EPI>   // EPI 0: bias + ReLU, 1: multiply by (mask > 0)
+__global__ void __launch_bounds__(128)
+edge_gather_kernel(const float4* __restrict__ big4, const float* __restrict__ w, const float* __restrict__ bias,
+                   const float* __restrict__ mask, float* __restrict__ small, long long npairs) {
+    __shared__ __align__(16) float ws[16 * CB * SC];
+    for (int i = threadIdx.x; i < 16 * CB * SC; i += blockDim.x) ws[i] = w[i];
+    __syncthreads();
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= npairs) return;
+    constexpr int PW = (SW + 1) / 2;                     // 40 pairs per output row
+    const int px = (int)(t % PW);
+    const int oy = (int)((t / PW) % SH);
+    const long long n = t / (PW * SH);
+    const int ox = px * 2;
+    const bool second = ox + 1 < SW;
+
+    float acc0[SC], acc1[SC];
+#pragma unroll
+    for (int j = 0; j < SC; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+
+    const float4* row0 = big4 + (n * EH + 2 * oy) * EW + 2 * ox;
+#pragma unroll
+    for (int kh = 0; kh < 4; ++kh) {
+        float4 in[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) in[q] = (q < 4 || second) ? __ldg(row0 + kh * EW + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int kw = 0; kw < 4; ++kw) {
+#pragma unroll
+            for (int c = 0; c < CB; ++c) {
+                const float a0 = c == 0 ? in[kw].x : (c == 1 ? in[kw].y : in[kw].z);
+                const float a1 = c == 0 ? in[kw + 2].x : (c == 1 ? in[kw + 2].y : in[kw + 2].z);
+                const float* wr = &ws[((kh * 4 + kw) * CB + c) * SC];
+#pragma unroll
+                for (int j4 = 0; j4 < SC / 4; ++j4) {
+                    const float4 wv = *reinterpret_cast<const float4*>(wr + j4 * 4);
+                    acc0[j4 * 4 + 0] = fmaf(a0, wv.x, acc0[j4 * 4 + 0]); acc1[j4 * 4 + 0] = fmaf(a1, wv.x, acc1[j4 * 4 + 0]);
+                    acc0[j4 * 4 + 1] = fmaf(a0, wv.y, acc0[j4 * 4 + 1]); acc1[j4 * 4 + 1] = fmaf(a1, wv.y, acc1[j4 * 4 + 1]);
+                    acc0[j4 * 4 + 2] = fmaf(a0, wv.z, acc0[j4 * 4 + 2]); acc1[j4 * 4 + 2] = fmaf(a1, wv.z, acc1[j4 * 4 + 2]);
+                    acc0[j4 * 4 + 3] = fmaf(a0, wv.w, acc0[j4 * 4 + 3]); acc1[j4 * 4 + 3] = fmaf(a1, wv.w, acc1[j4 * 4 + 3]);
+                }
+            }
+        }
+    }
+    const long long off = ((n * SH + oy) * SW + ox) * SC;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        if (half == 1 && !second) break;
+        float* acc = half == 0 ? acc0 : acc1;
+        const long long o = off + half * SC;
+#pragma unroll
+        for (int j4 = 0; j4 < SC / 4; ++j4) {
+            float4 v = make_float4(acc[j4 * 4], acc[j4 * 4 + 1], acc[j4 * 4 + 2], acc[j4 * 4 + 3]);
+            if (EPI == 0) {
+                const float4 b = *reinterpret_cast<const float4*>(bias + j4 * 4);
+                v.x = fmaxf(v.x + b.x, 0.f); v.y = fmaxf(v.y + b.y, 0.f); v.z = fmaxf(v.z + b.z, 0.f); v.w = fmaxf(v.w + b.w, 0.f);
+            } else {
+                const float4 mk = __ldg(reinterpret_cast<const float4*>(mask + o + j4 * 4));
+                v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f; v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
+            }
+            *reinterpret_cast<float4*>(small + o + j4 * 4) = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int WG_WARPS = 8;
+constexpr int BIG_ROW_FLOATS = EW * 4;            // 640 floats per padded big row
+constexpr int SMALL_ROW_FLOATS = SW * SC;         // 2528 floats per small row
+
+template <int CB>
+__global__ void __launch_bounds__(WG_WARPS * 32)
+edge_wgrad_kernel(const float* __restrict__ big4, const float* __restrict__ small, long long nrows, int rows_per_cta,
+                  float* __restrict__ partial) {
+    // micro-tile: lane = (ig, jg): ig in [0, NI) owns TI rows of the [16*CB x 32] tile, jg in [0, 8) owns 4 columns
+    constexpr int I = 16 * CB;                     // 48 or 16 rows: i = (kh*4 + kw)*CB + c
+    constexpr int NI = 4, TI = I / NI;             // 12 or 4 rows per lane
+    constexpr int BIGP = BIG_ROW_FLOATS + 4;       // padded row pitch: the 4 kernel-row lane groups hit different banks
+    __shared__ __align__(16) float sbig[2][4 * BIGP];
+    __shared__ __align__(16) float ssmall[2][SMALL_ROW_FLOATS + 32];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ig = lane >> 3, jg = lane & 7;
+    const long long r_begin = (long long)blockIdx.x * rows_per_cta;
+    long long r_end = r_begin + rows_per_cta;
+    if (r_end > nrows) r_end = nrows;
+
+    float acc[TI][4];
+#pragma unroll
+    for (int a = 0; a < TI; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+
+    auto stage_row = [&](int buf, long long r) {
+        const long long n = r / SH;
+        const int oy = (int)(r - n * SH);
+        const float* gb = big4 + ((n * EH + 2 * oy) * EW) * 4;           // 4 consecutive padded rows of 640 floats
+        for (int f = tid; f < 4 * BIG_ROW_FLOATS / 4; f += WG_WARPS * 32) {
+            const int kh = f / (BIG_ROW_FLOATS / 4), q = f - kh * (BIG_ROW_FLOATS / 4);
+            cp_async16(&sbig[buf][kh * BIGP + q * 4], gb + f * 4, true);
+        }
+        const float* gs = small + r * SMALL_ROW_FLOATS;
+        for (int f = tid; f < SMALL_ROW_FLOATS / 4; f += WG_WARPS * 32) cp_async16(&ssmall[buf][f * 4], gs + f * 4, true);
+    };
+
+    if (r_begin < r_end) stage_row(0, r_begin);
+    cp_async_commit();
+    int buf = 0;
+    for (long long r = r_begin; r < r_end; ++r, buf ^= 1) {
+        if (r + 1 < r_end) stage_row(buf ^ 1, r + 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        // this warp's positions of the row: ox = warp, warp + 8, ...
+        for (int ox = warp; ox < SW; ox += WG_WARPS) {
+            const float4 g = *reinterpret_cast<const float4*>(&ssmall[buf][ox * SC + jg * 4]);
+            // lane group ig owns kernel row kh = ig: its TI = 4*CB values are the window row's 4 pixels x CB channels
+            const float4* wp = reinterpret_cast<const float4*>(&sbig[buf][ig * BIGP + 2 * ox * 4]);
+            float a[TI];
+#pragma unroll
+            for (int kw = 0; kw < 4; ++kw) {
+                const float4 px = wp[kw];
+                a[kw * CB] = px.x;
+                if (CB == 3) { a[kw * CB + 1] = px.y; a[kw * CB + 2] = px.z; }
+            }
+#pragma unroll
+            for (int q = 0; q < TI; ++q) {
+                acc[q][0] = fmaf(a[q], g.x, acc[q][0]); acc[q][1] = fmaf(a[q], g.y, acc[q][1]);
+                acc[q][2] = fmaf(a[q], g.z, acc[q][2]); acc[q][3] = fmaf(a[q], g.w, acc[q][3]);
+            }
+        }
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+    // ---- combine the 8 warps: each warp adds its tile into shared memory in turn (fixed order -> deterministic)
+    float* tile = &sbig[0][0];                                  // reuse: I*32 floats <= 1536 < 4*BIGP
+    __syncthreads();
+    for (int w8 = 0; w8 < WG_WARPS; ++w8) {
+        if (warp == w8) {
+#pragma unroll
+            for (int q = 0; q < TI; ++q)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    float* dst = &tile[(ig * TI + q) * SC + jg * 4 + b];
+                    *dst = (w8 == 0 ? 0.f : *dst) + acc[q][b];
+                }
+        }
+        __syncthreads();
+    }
+    for (int f = tid; f < I * SC; f += WG_WARPS * 32) partial[(long long)blockIdx.x * I * SC + f] = tile[f];
+}
+
+}  // namespace
+
+int32_t launch_edge_gather(const float* big4, int cb, const float* w, const float* bias, const float* mask,
+                           float* small, int batch, cudaStream_t stream) {
+    CPB_REQUIRE(cb == 1 || cb == 3, "edge_gather: channels must be 1 or 3");
+    const long long npairs = (long long)batch * SH * ((SW + 1) / 2);
+    if (npairs == 0) return CPB_OK;
+    const unsigned blocks = (unsigned)cdiv(npairs, 128);
+    const float4* b4 = reinterpret_cast<const float4*>(big4);
+    if (mask == nullptr) {
+        if (cb == 3) edge_gather_kernel<3, 0><<<blocks, 128, 0, stream>>>(b4, w, bias, nullptr, small, npairs);
+        else edge_gather_kernel<1, 0><<<blocks, 128, 0, stream>>>(b4, w, bias, nullptr, small, npairs);
+    } else {
+        if (cb == 3) edge_gather_kernel<3, 1><<<blocks, 128, 0, stream>>>(b4, w, nullptr, mask, small, npairs);
+        else edge_gather_kernel<1, 1><<<blocks, 128, 0, stream>>>(b4, w, nullptr, mask, small, npairs);
+    }
+    CPB_LAUNCHED();
+    return CPB_OK;
+}
+
+int edge_wgrad_ctas(int batch) {
+    const long long nrows = (long long)batch * SH;
+    long long ctas = 148 * 2;
+    if (ctas > nrows) ctas = nrows;
+    return (int)(ctas < 1 ? 1 : ctas);
+}
+
+int32_t launch_edge_wgrad(const float* big4, int cb, const float* small, int batch, float* partial, cudaStream_t stream) {
+    CPB_REQUIRE(cb == 1 || cb == 3, "edge_wgrad: channels must be 1 or 3");
+    const long long nrows = (long long)batch * SH;
+    if (nrows == 0) return CPB_OK;
+    const int ctas = edge_wgrad_ctas(batch);
+    const int rows_per_cta = (int)((nrows + ctas - 1) / ctas);
+    if (cb == 3) edge_wgrad_kernel<3><<<ctas, WG_WARPS * 32, 0, stream>>>(big4, small, nrows, rows_per_cta, partial);
+    else edge_wgrad_kernel<1><<<ctas, WG_WARPS * 32, 0, stream>>>(big4, small, nrows, rows_per_cta, partial);
+    CPB_LAUNCHED();
+    return CPB_OK;
+}
+
+}  // namespace cpb

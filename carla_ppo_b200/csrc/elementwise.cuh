@@ -15,6 +15,14 @@ int32_t launch_prep_frames(const void* src, int dtype, float scale, int cin, lon
 int32_t launch_deconv4_fwd(const float* small, const float* w /*[4,4,Ct,32]*/, const float* bias, int batch,
                            int ct, float* logits_p, float* sigm, cudaStream_t stream);
 
+// 3-channel edge layers (edge.cu): big4 = float4-per-pixel padded image [B,80,160,4], small [B,39,79,32], w = TF kernel [4,4,cb,32]
+// gather: conv1 forward (mask == nullptr: bias + ReLU) / deconv4 data-gradient (mask != nullptr: ReLU mask, no bias)
+int32_t launch_edge_gather(const float* big4, int cb, const float* w, const float* bias, const float* mask,
+                           float* small, int batch, cudaStream_t stream);
+// weight gradient: partial[edge_wgrad_ctas(batch)][16*cb][32]; reduce with launch_reduce_partials
+int edge_wgrad_ctas(int batch);
+int32_t launch_edge_wgrad(const float* big4, int cb, const float* small, int batch, float* partial, cudaStream_t stream);
+
 // heads [2][B][z] (mean block, logvar block), eps [B,z] or nullptr -> zout [B,z], kl_rows [B],
 // kl_active [B] (1 when the KL term of that row has a gradient, i.e. above the tolerance floor).
 int32_t launch_reparam(const float* heads, const float* eps, int batch, int zdim, float kl_tolerance,

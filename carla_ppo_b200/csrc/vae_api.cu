@@ -186,7 +186,7 @@ static int64_t max_partial_floats(int B, int z) {
         {FEAT, z, (long long)B},                    // heads
         {z, FEAT, (long long)B},                    // dense1
     };
-    int64_t best = 0;
+    int64_t best = (int64_t)edge_wgrad_ctas(B) * 48 * C1;
     for (const P& p : ps) {
         int64_t n = (int64_t)wgrad_pick_splits(p.I, p.J, p.M) * p.I * p.J;
         if (n > best) best = n;
@@ -410,7 +410,6 @@ static int32_t relayout_weights(const VaePlan& pl, const VaeLayout& L, const flo
         j.count = mode == 0 ? (long long)taps * rows * cols : (long long)taps * rows_pad * cols;
         t.total += j.count;
     };
-    add(L.off[T_CONV1_K], pl.rl.conv1P, 16, 3, C1, 1, 4);
     if (decoder) {
         add(L.off[T_DECONV1_K], pl.rl.deconv1T, 16, C3, C4, 0, 0);
         add(L.off[T_DECONV2_K], pl.rl.deconv2T, 16, C2, C3, 0, 0);
@@ -422,7 +421,6 @@ static int32_t relayout_weights(const VaePlan& pl, const VaeLayout& L, const flo
         add(L.off[T_CONV4_K], pl.rl.conv4T, 16, C3, C4, 0, 0);
         add(L.off[T_DENSE1_K], pl.rl.dense1T, 1, pl.z, FEAT, 0, 0);
         add(L.off[T_MEAN_K], pl.rl.headsT, 2, FEAT, pl.z, 0, 0);   // mean and logvar kernels are adjacent
-        add(L.off[T_DECONV4_K], pl.rl.deconv4P, 16, pl.ct, C1, 1, 4);
     }
     ProfScope prof("relayout_weights", s);
     CPB_TRY(launch_relayout(params, pl.relayout, t, s));
@@ -462,9 +460,9 @@ static int32_t run_encoder(const VaePlan& pl, const VaeLayout& L, const cpb_vae_
     const float sscale = cfg->source_dtype == CPB_FRAME_U8 ? 1.f / 255.f : 1.f;
     { ProfScope prof("prep_frames", s);
       CPB_TRY(launch_prep_frames(source, cfg->source_dtype, sscale, 3, (long long)B * NPIX, pl.xp, flags, 1, s)); }
-    TapGemmParams p = gather_problem(pl.xp, B, H0, W0, 4, 4, pl.relayout + pl.rl.conv1P, C1,
-                                     params + L.off[T_CONV1_B], nullptr, pl.a1, 1);
-    CPB_TRY(tg("conv1.fwd", p, s));
+    { ProfScope prof("conv1.fwd", s);
+      CPB_TRY(launch_edge_gather(pl.xp, 3, params + L.off[T_CONV1_K], params + L.off[T_CONV1_B], nullptr, pl.a1, B, s)); }
+    TapGemmParams p;
     p = gather_problem(pl.a1, B, H1, W1, C1, 4, params + L.off[T_CONV2_K], C2, params + L.off[T_CONV2_B], nullptr, pl.a2, 1,
                        pl.relayout + pl.rl.tc[TC_CONV2].f_hi, pl.relayout + pl.rl.tc[TC_CONV2].f_lo);
     CPB_TRY(tg("conv2.fwd", p, s));
@@ -538,11 +536,14 @@ static int32_t run_backward(const VaePlan& pl, const VaeLayout& L, const cpb_vae
     float* cs = pl.colsum;
     CPB_TRY(launch_fill_zero(grads, L.total, s));
     // ---- deconv4 (padded to 4 channels on the big side)
-    CPB_TRY(run_wgrad("deconv4.wgrad", dlog, W0, 4, (long long)NPIX * 4, 4, pl.b3, B, H1, W1, C1, 4, pl.ct, pl.partial,
-                      grads + L.off[T_DECONV4_K], s));
+    { ProfScope prof("deconv4.wgrad", s);
+      CPB_TRY(launch_edge_wgrad(dlog, pl.ct, pl.b3, B, pl.partial, s));
+      CPB_TRY(launch_reduce_partials(pl.partial, edge_wgrad_ctas(B), 16 * pl.ct, C1, 16 * pl.ct, 16 * pl.ct,
+                                     grads + L.off[T_DECONV4_K], s)); }
     CPB_TRY(launch_colsum(dlog, (long long)B * NPIX, 4, pl.ct, grads + L.off[T_DECONV4_B], cs, s));
-    TapGemmParams p = gather_problem(dlog, B, H0, W0, 4, 4, pl.relayout + pl.rl.deconv4P, C1, nullptr, pl.b3, pl.gA, 0);
-    CPB_TRY(tg("deconv4.dgrad", p, s));                                   // gA = g(b3 pre-activation)
+    { ProfScope prof("deconv4.dgrad", s);
+      CPB_TRY(launch_edge_gather(dlog, pl.ct, params + L.off[T_DECONV4_K], nullptr, pl.b3, pl.gA, B, s)); }   // gA = g(b3 pre-activation)
+    TapGemmParams p;
     // ---- deconv3
     CPB_TRY(run_wgrad("deconv3.wgrad", pl.gA, W1, C1, (long long)H1 * W1 * C1, 5, pl.b2, B, H2, W2, C2, 5 * 5 * C1, 5 * 5 * C1,
                       pl.partial, grads + L.off[T_DECONV3_K], s));
@@ -605,8 +606,9 @@ static int32_t run_backward(const VaePlan& pl, const VaeLayout& L, const cpb_vae
                         pl.relayout + pl.rl.tc[TC_CONV2].t_hi, pl.relayout + pl.rl.tc[TC_CONV2].t_lo);
     CPB_TRY(tg("conv2.dgrad", p, s, 4));                                   // gB = g(a1)
     // ---- conv1 (its input gradient is never used: the reference computes and discards it)
-    CPB_TRY(run_wgrad("conv1.wgrad", pl.xp, W0, 4, (long long)NPIX * 4, 4, pl.gB, B, H1, W1, C1, 4, 3, pl.partial,
-                      grads + L.off[T_CONV1_K], s));
+    { ProfScope prof("conv1.wgrad", s);
+      CPB_TRY(launch_edge_wgrad(pl.xp, 3, pl.gB, B, pl.partial, s));
+      CPB_TRY(launch_reduce_partials(pl.partial, edge_wgrad_ctas(B), 48, C1, 48, 48, grads + L.off[T_CONV1_K], s)); }
     CPB_TRY(launch_colsum(pl.gB, (long long)B * H1 * W1, C1, C1, grads + L.off[T_CONV1_B], cs, s));
     return CPB_OK;
 }
