@@ -41,6 +41,11 @@ MAC = {"conv1": 4_732_416, "conv2": 22_413_312, "conv3": 18_874_368, "conv4": 12
        "deconv3": 35_020_800, "deconv4": 4_732_416}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the labelled kernel group, from the committed ncu --set full
+# capture profiles/r1_ncu_full_raw_tc.csv (B=4096, second train step)
+NCU_DRAM_BYTES_PER_LAUNCH = {"deconv3.wgrad": 2.3399e9, "conv2.fwd": 3.0326e9, "conv3.fwd": 1.3042e9}
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
@@ -158,15 +163,34 @@ def bench_ppo(steps=5):
             "ms_per_learn": ms, "config": {"workload": "T=2048 rollout x 67-d states, 4 epochs x 8 minibatches of 256, GAE+normalise+theta_old copy+32 Adam steps"}}
 
 
+def pick_cpu_threads(make_step, candidates=None):
+    """The GPU boxes expose 128 logical CPUs shared with other tenants; oneDNN on all of them is often far slower
+    than on a subset.  Time one step per candidate thread count and keep the fastest ("all the host threads it can
+    use" = as many as actually help)."""
+    import torch
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cands = candidates or sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu})
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        make_step()                      # warm-up at this thread count
+        t0 = time.perf_counter(); make_step(); dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    torch.set_num_threads(best)
+    return best
+
+
 def cpu_baseline_vae(seconds=12.0, micro=256):
     """torch-CPU fp32 restatement of the reference train step on a bounded sample (micro-batches of 256)."""
     import torch
     from oracle.torch_ref import TorchVAETrainer
     from oracle.vae_oracle import glorot_init
-    torch.set_num_threads(os.cpu_count() or 1)
     tr = TorchVAETrainer(glorot_init(0), lr=1e-4, loss_type="mse")
     g = torch.Generator(); g.manual_seed(0)
     x = torch.rand(micro, 80, 160, 3, generator=g); eps = torch.randn(micro, Z_DIM, generator=g)
+    xs, es = x[:64], eps[:64]
+    pick_cpu_threads(lambda: tr.step(xs, xs, es))
     tr.step(x, x, eps)                                   # warm-up
     n = 0
     t0 = time.perf_counter()
@@ -264,11 +288,15 @@ def run_ours(args):
             dom = max(conv_like, key=lambda k: conv_like[k]["ms_per_step"])
             ach = flops(dom) / (conv_like[dom]["ms_per_step"] * 1e-3) / 1e12
             total_ms = sum(v["ms_per_step"] for v in groups.values())
+            mode = int(lib.cpb_get_math_mode())
             roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["bf16_sustained"], "traffic": None,
+                    "frac": ach / peaks["bf16_sustained"], "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(dom),
                     "share_of_step": conv_like[dom]["ms_per_step"] / total_ms,
-                    "note": "fp32 SIMT FMA kernel (parity needs fp32-accurate math); peak quoted is the measured bf16 tensor "
-                            "figure (%s), fp32-FMA nominal peak is ~74 TFLOP/s" % peaks["source"],
+                    "math_mode": "tcgen05 kind::tf32, 3xTF32 split (fp32-accurate)" if mode == 1 else "fp32 SIMT FMA",
+                    "note": "achieved = algorithmic fp32-equivalent FLOPs of the layer / its CUDA-event time; peak = measured bf16 "
+                            "tensor figure (%s, sustained).  A 3xTF32 kernel issues 3 TF32 MMAs (half the bf16 rate) per algorithmic "
+                            "product, so its ceiling is peak/6 = %.0f TFLOP/s algorithmic; against that ceiling this kernel is at %.2f"
+                            % (peaks["source"], peaks["bf16_sustained"] / 6.0, ach / (peaks["bf16_sustained"] / 6.0)),
                     "step_hbm": {"bound": "hbm", "achieved": BYTES_PER_FRAME_TRAIN * GLOBAL_BATCH / (ms_step * 1e-3) / 1e9,
                                  "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                  "frac": BYTES_PER_FRAME_TRAIN * GLOBAL_BATCH / (ms_step * 1e-3) / 1e9 / peaks["hbm_gbs"]},
@@ -311,11 +339,11 @@ def run_reference(args):
     import torch
     from oracle.torch_ref import TorchVAETrainer
     from oracle.vae_oracle import glorot_init
-    torch.set_num_threads(os.cpu_count() or 1)
     sample, micro = 512, 256
     tr = TorchVAETrainer(glorot_init(0), lr=1e-4, loss_type="mse")
     g = torch.Generator(); g.manual_seed(0)
     x = torch.rand(sample, 80, 160, 3, generator=g); eps = torch.randn(sample, Z_DIM, generator=g)
+    pick_cpu_threads(lambda: tr.step(x[:64], x[:64], eps[:64]))
     for _ in range(max(1, min(args.warmup, 2))):
         tr.step(x, x, eps, micro_batch=micro)
     steps = max(1, min(args.steps, 20))
