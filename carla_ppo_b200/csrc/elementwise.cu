@@ -29,42 +29,51 @@ __global__ void prep_frames_kernel(const T* __restrict__ src, float scale, long 
 }
 
 // ------------------------------------------------------------------------------------------
-// output layer: conv2d_transpose 4x4 s2, 32 -> CT channels.  One thread = one 2x2 output quad.
+// output layer: conv2d_transpose 4x4 s2, 32 -> CT channels.  One thread = TWO horizontally adjacent 2x2 output
+// quads (qx0, qx0+1): they share the middle input pixel and, more importantly, every weight float4 read from
+// shared memory (warp-broadcast) now feeds 8 FMAs instead of 4.
 // ------------------------------------------------------------------------------------------
 template <int CT>
 __global__ void __launch_bounds__(128)
 deconv4_fwd_kernel(const float* __restrict__ small, const float* __restrict__ w, const float* __restrict__ bias,
-                   long long nquads, float* __restrict__ logits_p, float* __restrict__ sigm) {
-    constexpr int HS = 39, WS = 79, CS = 32, QH = 40, QW = 80, HB = 80, WB = 160;
+                   long long npairs, float* __restrict__ logits_p, float* __restrict__ sigm) {
+    constexpr int HS = 39, WS = 79, CS = 32, QH = 40, QW = 80, HB = 80, WB = 160, PW = QW / 2;
     __shared__ __align__(16) float ws[16 * CT * CS];
     for (int i = threadIdx.x; i < 16 * CT * CS; i += blockDim.x) ws[i] = w[i];
     __syncthreads();
-    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nquads) return;
-    const int qx = (int)(q % QW);
-    const int qy = (int)((q / QW) % QH);
-    const long long n = q / (QW * QH);
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= npairs) return;
+    const int qx0 = (int)(t % PW) * 2;
+    const int qy = (int)((t / PW) % QH);
+    const long long n = t / (PW * QH);
 
-    float acc[2][2][CT];
+    float acc[2][2][2][CT];     // [quad][py][px][c]
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
+    for (int q = 0; q < 2; ++q)
 #pragma unroll
-        for (int b = 0; b < 2; ++b)
+        for (int a = 0; a < 2; ++a)
 #pragma unroll
-            for (int c = 0; c < CT; ++c) acc[a][b][c] = bias[c];
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+                for (int c = 0; c < CT; ++c) acc[q][a][b][c] = bias[c];
 
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
         const int iy = qy - j;
         if (iy < 0 || iy >= HS) continue;
+        const float* rowp = small + ((n * HS + iy) * WS) * CS;
+        // input pixels p = qx0-1, qx0, qx0+1 ; quad q uses pixel (q + 1 - i) for tap column i
+        bool pv[3];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int ix = qx - i;
-            if (ix < 0 || ix >= WS) continue;
-            const float4* xp = reinterpret_cast<const float4*>(small + ((n * HS + iy) * WS + ix) * CS);
+        for (int p = 0; p < 3; ++p) pv[p] = (unsigned)(qx0 - 1 + p) < (unsigned)WS;
 #pragma unroll
-            for (int c4 = 0; c4 < CS / 4; ++c4) {
-                const float4 x = __ldg(xp + c4);
+        for (int c4 = 0; c4 < CS / 4; ++c4) {
+            float4 x[3];
+#pragma unroll
+            for (int p = 0; p < 3; ++p)
+                x[p] = pv[p] ? __ldg(reinterpret_cast<const float4*>(rowp + (qx0 - 1 + p) * CS) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
 #pragma unroll
                 for (int py = 0; py < 2; ++py)
 #pragma unroll
@@ -73,31 +82,36 @@ deconv4_fwd_kernel(const float* __restrict__ small, const float* __restrict__ w,
 #pragma unroll
                         for (int c = 0; c < CT; ++c) {
                             const float4 wv = *reinterpret_cast<const float4*>(&ws[(tap * CT + c) * CS + c4 * 4]);
-                            float s = acc[py][px][c];
-                            s = fmaf(x.x, wv.x, s); s = fmaf(x.y, wv.y, s);
-                            s = fmaf(x.z, wv.z, s); s = fmaf(x.w, wv.w, s);
-                            acc[py][px][c] = s;
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) {
+                                const float4 xv = x[q + 1 - i];
+                                float s = acc[q][py][px][c];
+                                s = fmaf(xv.x, wv.x, s); s = fmaf(xv.y, wv.y, s);
+                                s = fmaf(xv.z, wv.z, s); s = fmaf(xv.w, wv.w, s);
+                                acc[q][py][px][c] = s;
+                            }
                         }
                     }
-            }
         }
     }
 #pragma unroll
-    for (int py = 0; py < 2; ++py)
+    for (int q = 0; q < 2; ++q)
 #pragma unroll
-        for (int px = 0; px < 2; ++px) {
-            const long long pix = (n * HB + 2 * qy + py) * WB + 2 * qx + px;
-            if (logits_p != nullptr) {
-                float v[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int py = 0; py < 2; ++py)
 #pragma unroll
-                for (int c = 0; c < CT; ++c) v[c] = acc[py][px][c];
-                reinterpret_cast<float4*>(logits_p)[pix] = make_float4(v[0], v[1], v[2], v[3]);
+            for (int px = 0; px < 2; ++px) {
+                const long long pix = (n * HB + 2 * qy + py) * WB + 2 * (qx0 + q) + px;
+                if (logits_p != nullptr) {
+                    float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int c = 0; c < CT; ++c) v[c] = acc[q][py][px][c];
+                    reinterpret_cast<float4*>(logits_p)[pix] = make_float4(v[0], v[1], v[2], v[3]);
+                }
+                if (sigm != nullptr) {
+#pragma unroll
+                    for (int c = 0; c < CT; ++c) sigm[pix * CT + c] = 1.f / (1.f + expf(-acc[q][py][px][c]));
+                }
             }
-            if (sigm != nullptr) {
-#pragma unroll
-                for (int c = 0; c < CT; ++c) sigm[pix * CT + c] = 1.f / (1.f + expf(-acc[py][px][c]));
-            }
-        }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -353,11 +367,11 @@ int32_t launch_prep_frames(const void* src, int dtype, float scale, int cin, lon
 
 int32_t launch_deconv4_fwd(const float* small, const float* w, const float* bias, int batch, int ct,
                            float* logits_p, float* sigm, cudaStream_t stream) {
-    const long long nquads = (long long)batch * 40 * 80;
-    if (nquads == 0) return CPB_OK;
-    const unsigned blocks = (unsigned)cdiv(nquads, 128);
-    if (ct == 3) deconv4_fwd_kernel<3><<<blocks, 128, 0, stream>>>(small, w, bias, nquads, logits_p, sigm);
-    else if (ct == 1) deconv4_fwd_kernel<1><<<blocks, 128, 0, stream>>>(small, w, bias, nquads, logits_p, sigm);
+    const long long npairs = (long long)batch * 40 * 40;     // pairs of 2x2 output quads
+    if (npairs == 0) return CPB_OK;
+    const unsigned blocks = (unsigned)cdiv(npairs, 128);
+    if (ct == 3) deconv4_fwd_kernel<3><<<blocks, 128, 0, stream>>>(small, w, bias, npairs, logits_p, sigm);
+    else if (ct == 1) deconv4_fwd_kernel<1><<<blocks, 128, 0, stream>>>(small, w, bias, npairs, logits_p, sigm);
     else CPB_REQUIRE(false, "deconv4: target_channels must be 1 or 3");
     CPB_LAUNCHED();
     return CPB_OK;

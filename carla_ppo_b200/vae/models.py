@@ -514,6 +514,89 @@ class VAE:
             raise ValueError("verify_range: target_states outside [0, 1]")
         return float(losses[0]), float(losses[1])
 
+    class _PendingStep:
+        """Handle of a pipelined host-fed step: ``result()`` waits for it and returns (recon, kl)."""
+
+        def __init__(self, vae, slot):
+            self._vae, self._slot = vae, slot
+
+        def result(self):
+            st = self._vae._pipe
+            st["done"][self._slot].synchronize()
+            host = st["losses_host"][self._slot]
+            if int(host[2]) & 1:
+                raise ValueError("verify_range: source_states outside [0, 1]")
+            if int(host[2]) & 2:
+                raise ValueError("verify_range: target_states outside [0, 1]")
+            return float(host[0]), float(host[1])
+
+    def train_step_async(self, source, target=None, eps=None):
+        """Host-fed minibatch step with input prefetch: the H2D copy of THIS batch runs on a copy stream (two
+        device staging slots) while the previous step still computes; the step is enqueued behind it and the
+        losses come back through a pinned buffer.  Returns a handle; call ``.result()`` (typically one step
+        later) for (recon, kl).  ``source``/``target`` are host arrays or pinned CPU tensors (fp32 or uint8);
+        ``target=None`` or ``target is source`` means the rgb target == source."""
+        self._require_session()
+        torch = self._torch
+        if not self.training:
+            raise CpbError("this VAE was built with training=False")
+
+        def as_cpu_tensor(a, channels):
+            if not isinstance(a, torch.Tensor):
+                arr = np.asarray(a)
+                if arr.dtype != np.uint8:
+                    arr = arr.astype(np.float32, copy=False)
+                a = torch.from_numpy(np.ascontiguousarray(arr))
+            if tuple(a.shape[1:]) != (80, 160, channels):
+                raise ValueError("expected frames of shape [B,80,160,%d], got %r" % (channels, tuple(a.shape)))
+            return a
+        same = target is None or target is source
+        xs = as_cpu_tensor(source, 3)
+        ys = xs if same else as_cpu_tensor(target, self.target_shape[2])
+        b = xs.shape[0]
+        key = (b, xs.dtype, ys.dtype, same)
+        st = getattr(self, "_pipe", None)
+        if st is None or st["key"] != key:
+            dev = self._device
+            st = self._pipe = {
+                "key": key, "i": 0, "copy_stream": torch.cuda.Stream(device=dev),
+                "x": [torch.empty((b, 80, 160, 3), dtype=xs.dtype, device=dev) for _ in range(2)],
+                "y": [None, None] if same else [torch.empty((b, 80, 160, self.target_shape[2]), dtype=ys.dtype, device=dev) for _ in range(2)],
+                "eps": [torch.empty((b, self.z_dim), dtype=torch.float32, device=dev) for _ in range(2)],
+                "copied": [torch.cuda.Event() for _ in range(2)], "done": [torch.cuda.Event() for _ in range(2)],
+                "used": [False, False],
+                "losses_dev": [torch.zeros(3, dtype=torch.float32, device=dev) for _ in range(2)],
+                "losses_host": [torch.zeros(3, dtype=torch.float32).pin_memory() for _ in range(2)],
+            }
+        slot = st["i"] % 2
+        st["i"] += 1
+        compute = torch.cuda.current_stream()
+        cs = st["copy_stream"]
+        if st["used"][slot]:
+            cs.wait_event(st["done"][slot])            # the step that last read this slot has finished
+        with torch.cuda.stream(cs):
+            st["x"][slot].copy_(xs, non_blocking=True)
+            if not same:
+                st["y"][slot].copy_(ys, non_blocking=True)
+            if eps is not None:
+                e = eps if isinstance(eps, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(eps, np.float32))
+                st["eps"][slot].copy_(e, non_blocking=True)
+            st["copied"][slot].record(cs)
+        compute.wait_event(st["copied"][slot])
+        if eps is None:
+            st["eps"][slot].copy_(self._eps(b))
+        x = st["x"][slot]
+        y = x if same else st["y"][slot]
+        losses = self.train_step_device(x, y, st["eps"][slot])
+        ld = st["losses_dev"][slot]
+        ld[:2].copy_(losses)
+        ld[2:3].copy_(self._flags.to(torch.float32))
+        self._flags.zero_()
+        st["losses_host"][slot].copy_(ld, non_blocking=True)
+        st["done"][slot].record(compute)
+        st["used"][slot] = True
+        return VAE._PendingStep(self, slot)
+
     def _device_dataset(self, arr, channels):
         """Upload a host dataset once and keep it resident (keyed on the array's identity and buffer)."""
         torch = self._torch
