@@ -261,33 +261,52 @@ tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
             const int col0 = n0 + half * HALF_COLS;
             const long long img = (long long)n * p.dst_img;
             const long long off_plain = img + ((long long)(oy * p.dstride + cls.py) * p.Wd + (ox * p.dstride + cls.px)) * p.dst_pitch;
+            // groups of 4 columns, handled 4 at a time so that the ReLU-mask loads of a batch are all in flight
+            // together (one at a time they serialise 16 global round trips per thread)
+            constexpr int NG = HALF_COLS / 4;
+            constexpr int GB = NG < 4 ? NG : 4;
 #pragma unroll
-            for (int g = 0; g < HALF_COLS / 4; ++g) {
-                const int col = col0 + g * 4;
-                long long off;
-                int ch;
-                if (p.quad) {
-                    const int c = col / p.quad_cb;
-                    ch = col - c * p.quad_cb;
-                    const int y = oy * 2 + (c >> 1), x = ox * 2 + (c & 1);
-                    if (y >= p.Hd || x >= p.Wd) continue;
-                    off = img + ((long long)y * p.Wd + x) * p.dst_pitch + ch;
-                } else {
-                    ch = col;
-                    off = off_plain + col;
+            for (int g0 = 0; g0 < NG; g0 += GB) {
+                long long offs[GB];
+                int chs[GB];
+                bool oks[GB];
+                float4 mks[GB];
+#pragma unroll
+                for (int u = 0; u < GB; ++u) {
+                    const int col = col0 + (g0 + u) * 4;
+                    oks[u] = true;
+                    if (p.quad) {
+                        const int c = col / p.quad_cb;
+                        chs[u] = col - c * p.quad_cb;
+                        const int y = oy * 2 + (c >> 1), x = ox * 2 + (c & 1);
+                        oks[u] = y < p.Hd && x < p.Wd;
+                        offs[u] = img + ((long long)y * p.Wd + x) * p.dst_pitch + chs[u];
+                    } else {
+                        chs[u] = col;
+                        offs[u] = off_plain + col;
+                    }
                 }
-                float4 o = make_float4(acc[g * 4 + 0], acc[g * 4 + 1], acc[g * 4 + 2], acc[g * 4 + 3]);
-                if (p.bias) {
-                    const float4 b = *reinterpret_cast<const float4*>(p.bias + ch);
-                    o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                }
-                if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                 if (p.mask) {
-                    const float4 mk = *reinterpret_cast<const float4*>(p.mask + off);
-                    o.x = mk.x > 0.f ? o.x : 0.f; o.y = mk.y > 0.f ? o.y : 0.f;
-                    o.z = mk.z > 0.f ? o.z : 0.f; o.w = mk.w > 0.f ? o.w : 0.f;
+#pragma unroll
+                    for (int u = 0; u < GB; ++u)
+                        mks[u] = oks[u] ? __ldg(reinterpret_cast<const float4*>(p.mask + offs[u])) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                *reinterpret_cast<float4*>(p.dst + off) = o;
+#pragma unroll
+                for (int u = 0; u < GB; ++u) {
+                    if (!oks[u]) continue;
+                    const int g = g0 + u;
+                    float4 o = make_float4(acc[g * 4 + 0], acc[g * 4 + 1], acc[g * 4 + 2], acc[g * 4 + 3]);
+                    if (p.bias) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + chs[u]));
+                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                    }
+                    if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    if (p.mask) {
+                        o.x = mks[u].x > 0.f ? o.x : 0.f; o.y = mks[u].y > 0.f ? o.y : 0.f;
+                        o.z = mks[u].z > 0.f ? o.z : 0.f; o.w = mks[u].w > 0.f ? o.w : 0.f;
+                    }
+                    *reinterpret_cast<float4*>(p.dst + offs[u]) = o;
+                }
             }
         }
     }

@@ -75,11 +75,13 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
     const uint32_t tmem_base = tmem_slot;
 
     // ---- loader: thread = (channel group cg of 4 channels, position block mb of 4 reduction positions).
-    //      A quarter-warp holds 2 adjacent channel groups x 4 position blocks: its 8 swizzled chunk slots
-    //      (mb ^ row%8, rows r and r+4) are distinct -> conflict-free STS.128; a warp's LDG.128 covers 4 rows x
-    //      128 contiguous bytes (8 channel groups) -> fully coalesced.
-    const int cg = (warp >> 1) * 8 + ((lane >> 3) & 3) * 2 + ((lane >> 2) & 1);
-    const int mb = (warp & 1) * 4 + (lane & 3);
+    //      A quarter-warp = 8 consecutive channel groups of ONE position: its LDG.128 is one contiguous 128-byte
+    //      line (the L1 data pipe charges a wavefront per 32-byte sector when a quarter-warp straddles lines).
+    //      Conflict-free stores then need the 8 lanes to hit 8 different swizzle slots: channel 4*cg + c is kept in
+    //      tile row rho = 32*c + cg (A) / (BN/4)*c + cg (B), so a quarter-warp's rows differ in rho%8.  The
+    //      accumulator rows / columns come out permuted the same way and are un-permuted when the partial is stored.
+    const int cg = (warp & 3) * 8 + (lane & 7);
+    const int mb = (warp >> 2) * 4 + (lane >> 3);
     const int a_i = i0 + cg * 4;
     const bool a_col_ok = a_i < p.I;
     long long a_coloff = 0;
@@ -87,13 +89,15 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
         const int tap = a_i / p.run;
         a_coloff = p.tap_off[tap] + (a_i - tap * p.run);
     }
-    const bool b_col_ok = cg * 4 < BN;
-    // swizzled chunk address of (row r = cg*4 + c, 16-byte chunk mb): rows 4cg..4cg+3 share the 1 KB group
-    uint32_t soff[4];
+    constexpr int BQ = BN / 4;                       // channel groups of the B tile
+    const bool b_col_ok = cg < BQ;
+    uint32_t soff[4], soffb[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        const int r = cg * 4 + c;
-        soff[c] = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((mb ^ (r & 7)) << 4));
+        const int ra = 32 * c + cg;
+        soff[c] = (uint32_t)((ra >> 3) * 1024 + (ra & 7) * 128 + ((mb ^ (ra & 7)) << 4));
+        const int rb = BQ * c + (cg % BQ);
+        soffb[c] = (uint32_t)((rb >> 3) * 1024 + (rb & 7) * 128 + ((mb ^ (rb & 7)) << 4));
     }
 
     float4 areg[4], breg[4];
@@ -117,7 +121,7 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
     };
 
     // 4x4 register transpose + split + store: x[j] = 4 channels at position j  ->  one chunk per channel
-    auto store_t = [&](uint32_t tile_hi, uint32_t tile_lo, const float4* x) {
+    auto store_t = [&](uint32_t tile_hi, uint32_t tile_lo, const float4* x, const uint32_t* so) {
         const float xs[4][4] = {{x[0].x, x[1].x, x[2].x, x[3].x}, {x[0].y, x[1].y, x[2].y, x[3].y},
                                 {x[0].z, x[1].z, x[2].z, x[3].z}, {x[0].w, x[1].w, x[2].w, x[3].w}};
 #pragma unroll
@@ -125,8 +129,8 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
             float4 hi, lo;
             split_tf32(xs[c][0], hi.x, lo.x); split_tf32(xs[c][1], hi.y, lo.y);
             split_tf32(xs[c][2], hi.z, lo.z); split_tf32(xs[c][3], hi.w, lo.w);
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(tile_hi + soff[c]), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(tile_lo + soff[c]), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(tile_hi + so[c]), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(tile_lo + so[c]), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
         }
     };
 
@@ -164,8 +168,8 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
         if (kb % CHUNK_KB == 0) {
             while (drained < kb / CHUNK_KB - 1) drain_one();
         }
-        store_t(stage, stage + A_TILE_BYTES, areg);
-        if (b_col_ok) store_t(stage + 2 * A_TILE_BYTES, stage + 2 * A_TILE_BYTES + B_TILE_BYTES, breg);
+        store_t(stage, stage + A_TILE_BYTES, areg, soff);
+        if (b_col_ok) store_t(stage + 2 * A_TILE_BYTES, stage + 2 * A_TILE_BYTES + B_TILE_BYTES, breg, soffb);
         if (kb + 1 < nkb) load_regs(kb + 1);
 
         fence_async_smem();
@@ -205,14 +209,16 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
             for (int i = 0; i < 16; ++i) acc[cc + i] += v[i];
         }
     }
-    // ---- partial[split][i][j]
+    // ---- partial[split][i][j]: TMEM lane rho = q*32 + lane holds channel i = 4*lane + q; accumulator column
+    //      rho_b = half*BN/2 + a holds j = 4*(rho_b % BQ) + rho_b / BQ, i.e. this thread has the column pairs
+    //      (4*cgb + 2*half, +1) for every cgb
     {
-        const int i = i0 + q * 32 + lane;
+        const int i = i0 + 4 * lane + q;
         if (i < p.I) {
-            float* out = p.partial + ((long long)blockIdx.z * p.I + i) * p.J + j0 + half * HALF_COLS;
+            float* out = p.partial + ((long long)blockIdx.z * p.I + i) * p.J + j0 + 2 * half;
 #pragma unroll
-            for (int g = 0; g < HALF_COLS / 4; ++g)
-                *reinterpret_cast<float4*>(out + g * 4) = make_float4(acc[g * 4 + 0], acc[g * 4 + 1], acc[g * 4 + 2], acc[g * 4 + 3]);
+            for (int cgb = 0; cgb < BQ; ++cgb)
+                *reinterpret_cast<float2*>(out + 4 * cgb) = make_float2(acc[cgb], acc[BQ + cgb]);
         }
     }
     tc_fence_before();
