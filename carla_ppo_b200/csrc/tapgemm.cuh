@@ -62,6 +62,9 @@ struct TapGemmParams {
     // weight blocks carry zeros where a class does not use a tap.  The A tile is loaded once for all four classes.
     int quad;
     int quad_cb;
+    int quad_lcb;         // log2(quad_cb), set by the launcher
+    int cluster;          // tensor-core path: CTAs per cluster (set by the launcher)
+    int debug;            // tensor-core path: timing decomposition (CPB_TC_DEBUG): 1 no MMA, 2 no A stores, 4 no A loads, 8 no B copies
     TapClass cls[4];
 };
 
@@ -73,12 +76,15 @@ int32_t tapgemm_init();
 // ---- tcgen05 (3xTF32) variant of the same contraction -------------------------------------------------
 struct TcWeightJob {
     long long src_off;          // float offset of the TF kernel [k,k,Cb,Cs] in the parameter buffer
-    long long dst_hi, dst_lo;   // float offsets in the tensor-core weight buffer
-    int mode;                   // 0: plain copy; 1: gather form [kh][cs][kw*Cb+cb];
+    long long dst_hi, dst_lo;   // float offset of the operand (2 * taps * N * C floats, hi and lo interleaved by block) / unused
+    int mode;                   // logical operand per tap [N][C]:  0: plain K-major matrix; 1: gather form [kh][cs][kw*Cb+cb];
                                 // 2: quad scatter form [j][i][class*Cb+cb][cs], window w = (k+1)/2, zero where unused
     int k, cb, cs;
+    int N, C;                   // logical rows / reduction length per tap
     long long count;
 };
+// rows of the N axis handled per CTA tile (also fixes the block size of the stored operand)
+__host__ __device__ constexpr int tc_bn(int N) { return N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 32); }
 constexpr int kMaxTcWeightJobs = 12;
 struct TcWeightTable {
     int njobs;

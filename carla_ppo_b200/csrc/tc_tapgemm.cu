@@ -17,10 +17,10 @@
 // K=4096; scripts/diag_tc.py).  Two measures bring this back to fp32-FMA level:
 //   * the two cross terms (2^-11 of the main term) accumulate in their OWN TMEM tile, so they no longer
 //     re-truncate the large accumulator twice per k-step;
-//   * the main term is accumulated in TMEM only over chunks of 128 k (4 k-blocks, 16 MMAs) into two ping-pong
-//     tiles; each finished chunk is drained with tcgen05.ld and added to per-thread fp32 REGISTER accumulators
-//     (round-to-nearest).  The drain of chunk j is issued one chunk late, when its MMAs have long retired, so it
-//     never stalls the loaders.
+//   * accumulation inside TMEM only runs over chunks of 128 k (4 k-blocks, 16 + 32 MMAs) into two ping-pong
+//     (main | cross) buffers; each finished chunk is drained with tcgen05.ld and added to per-thread fp32
+//     REGISTER accumulators (round-to-nearest).  The drain of chunk j is issued one chunk late, when its MMAs
+//     have long retired, so it never stalls the loaders.
 // The register accumulators feed the bias / ReLU / ReLU-mask epilogue directly.
 #include "tapgemm.cuh"
 #include "tc_common.cuh"
@@ -37,145 +37,254 @@ struct TcCfg {
     static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
     static constexpr int STAGES = (STAGE_BYTES * 4 <= 200 * 1024) ? 4 : ((STAGE_BYTES * 3 <= 200 * 1024) ? 3 : 2);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;   // +1024: manual 1 KB alignment
-    static constexpr int TMEM_COLS = BN == 128 ? 512 : (BN == 64 ? 256 : 128);   // 2 main tiles + 1 cross tile, power of 2
+    static constexpr int TMEM_COLS = 4 * BN;                         // 2 x (main tile | cross tile): 512 / 256 / 128
 };
 constexpr int CHUNK_KB = 4;   // k-blocks accumulated inside TMEM before draining to registers (must be >= STAGES)
 
-constexpr int kLoaderThreads = 256;   // warps 0-7: loaders, accumulator drain, epilogue
-constexpr int kTcThreads = 288;       // + warp 8: MMA issuer (one elected lane)
+constexpr int kLoaderWarps = 8;                       // warps 0-7: A loaders, accumulator drain, epilogue
+constexpr int kIssuerWarp = 8;                        // warp 8: MMA issuer (one elected lane)
+constexpr int kWeightWarp = 9;                        // warp 9: weight-tile producer (bulk copies, one elected lane)
+constexpr int kTcThreads = 320;
 
-template <int BN>
+int g_tc_cluster = 1;         // CTAs per cluster = multicast width of the weight tiles (CPB_TC_CLUSTER, 1/2/4/8)
+int g_tc_clusters[3] = {0, 0, 0};   // co-resident clusters of the persistent grid, per BN instantiation (32/64/128)
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_count_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy (TMA engine, no tensor map), completion counted in bytes on an mbarrier; with a CTA
+// mask the same bytes land at the same shared offsets (data and barrier) of every CTA of the cluster in the mask
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask, bool multicast) {
+    if (multicast)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                     ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask) : "memory");
+    else
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask, bool multicast) {
+    if (multicast)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+    else
+        umma_commit(bar);
+}
+
+// PROF: per-phase clock64 accounting, printed by CTA 0 (CPB_TC_DEBUG & 16; instrumented instantiation)
+#define TC_PROF(slot) do { if constexpr (PROF) { const long long now_ = clock64(); prof[slot] += now_ - tlast; tlast = now_; } } while (0)
+
+// PERSISTENT, CLUSTERED kernel.  A cluster of CS CTAs works on super-tiles (class z, n-tile y, group of CS m-tiles):
+// CTA r of the cluster owns m-tile CS*xs + r, and all CS CTAs need the SAME weight tiles in the same order.  Each
+// k-block's weight tile (pre-split hi | lo, stored in global memory as the ready-made swizzled shared-memory image,
+// tc_weights_kernel) is therefore fetched ONCE per cluster: CTA r bulk-copies slice r of it and the copy engine
+// multicasts the slice into every CTA's stage.  Without this, every SM pulls the same 2*BN*128 bytes per k-block
+// through L2 -- twice the activation traffic, all SMs on the same few L2 slices at the same time -- and the kernel
+// is L2-bound at a third of the tensor-core rate.
+// The k-blocks of all super-tiles of a cluster form one stream through the stage ring and the two TMEM accumulator
+// buffers; a chunk never spans two tiles.  Chunk c is drained (one chunk late) while the tensor core already runs
+// chunk c+1 -- also across a tile boundary, so the bias / ReLU / mask epilogue of tile t and the first loads of
+// tile t+1 overlap the MMAs.
+template <int BN, bool PROF>
 __global__ void __launch_bounds__(kTcThreads, 1)
-tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
+tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p, const int mgroups, const int total_st) {
     using Cfg = TcCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int B_TILE_BYTES = Cfg::B_TILE_BYTES;
     constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
-    constexpr int B_CHUNKS = BN * 8;                 // 16-byte chunks per B tile
-    constexpr int B_ITERS = (B_CHUNKS + 255) / 256;
     static_assert(STAGES <= CHUNK_KB, "late drain relies on the stage ring being no deeper than a chunk");
 
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[STAGES];     // loaders -> issuer: stage holds A(hi,lo) and B(hi,lo) of a k-block
-    __shared__ uint64_t empty_bar[STAGES];    // tensor core -> loaders: the MMAs reading the stage retired
-    __shared__ uint64_t chunk_bar[2];         // tensor core -> loaders: main tile b holds a finished 128-k chunk
-    __shared__ uint64_t drained_bar[2];       // loaders -> issuer: main tile b was added to the register accumulators
-    __shared__ uint64_t done_bar;
+    __shared__ uint64_t full_bar[STAGES];     // A loader warps + weight bytes -> issuer
+    __shared__ uint64_t empty_bar[STAGES];    // tensor cores of ALL CTAs of the cluster -> producers: stage is free everywhere
+    __shared__ uint64_t chunk_bar[2];         // tensor core -> loaders: accumulator buffer b holds a finished chunk
+    __shared__ uint64_t drained_bar[2];       // loader warps -> issuer: buffer b was added to the register accumulators
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const TapClass& cls = p.cls[blockIdx.z];
-    const int Wo = cls.Wo;
-    const int HoWo = cls.Ho * Wo;
-    const long long M = (long long)p.batch * HoWo;
-    const long long m0 = (long long)blockIdx.x * TBM;
-    if (m0 >= M) return;                              // uniform per CTA: safe before any barrier / alloc
-    const int n0 = blockIdx.y * BN;
+    const int ntn = p.N / BN;
+    const int CS = (int)p.cluster;
+    const int rank = CS > 1 ? (int)cluster_ctarank() : 0;
+    const int cl_id = CS > 1 ? (int)cluster_id_x() : (int)blockIdx.x;
+    const int cl_n = CS > 1 ? (int)cluster_count_x() : (int)gridDim.x;
+    const uint16_t cl_mask = (uint16_t)((1u << CS) - 1u);
+    // the dynamic shared window starts at the same offset in every CTA of the kernel, so the 1 KB-aligned base is
+    // the same offset everywhere -- which the multicast copies rely on
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], kLoaderThreads); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], kLoaderWarps + 1); mbar_init(&empty_bar[s], (uint32_t)CS); }
         mbar_init(&chunk_bar[0], 1); mbar_init(&chunk_bar[1], 1);
-        mbar_init(&drained_bar[0], kLoaderThreads); mbar_init(&drained_bar[1], kLoaderThreads);
-        mbar_init(&done_bar, 1);
+        mbar_init(&drained_bar[0], kLoaderWarps); mbar_init(&drained_bar[1], kLoaderWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc<Cfg::TMEM_COLS>(&tmem_slot);
     tc_fence_before();
     __syncthreads();
+    if (CS > 1) cluster_sync_all();             // peers' barriers are initialised before anything is sent to them
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
 
-    const int nkb = cls.ntaps * (p.C / TBK);
-    const int nchunks = (nkb + CHUNK_KB - 1) / CHUNK_KB;
+    // super-tile st -> (class z, m-group xs, n-tile y), n fastest: clusters running side by side share the A rows through L2
+    auto st_z = [&](int st) { return st / (ntn * mgroups); };
+    auto st_y = [&](int st) { return st % ntn; };
+    auto st_m0 = [&](int st) { return (long long)(((st / ntn) % mgroups) * CS + rank) * TBM; };
+    const int kb_per_tap = p.C / TBK;
 
-    if (warp == 8) {
+    if (warp == kIssuerWarp) {
         // ================================ MMA issuer ================================
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
-            const uint32_t d_cross = tmem_base + (uint32_t)(2 * BN);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t stage = smem_base + s * STAGE_BYTES;
-                const int chunk = kb / CHUNK_KB;
-                mbar_wait(&full_bar[s], (uint32_t)((kb / STAGES) & 1));
-                if (kb % CHUNK_KB == 0 && chunk >= 2)      // main tile (chunk & 1) must have been drained (chunk - 2)
-                    mbar_wait(&drained_bar[chunk & 1], (uint32_t)(((chunk >> 1) - 1) & 1));
-                tc_fence_after();
-                const uint64_t a_hi = make_desc(stage);
-                const uint64_t a_lo = make_desc(stage + A_TILE_BYTES);
-                const uint64_t b_hi = make_desc(stage + 2 * A_TILE_BYTES);
-                const uint64_t b_lo = make_desc(stage + 2 * A_TILE_BYTES + B_TILE_BYTES);
-                const uint32_t d_main = tmem_base + (uint32_t)((chunk & 1) * BN);
+            int g = 0, gc = 0;                  // k-blocks / chunks issued so far (all tiles)
+            long long prof[4] = {0, 0, 0, 0}, tlast = 0;
+            if constexpr (PROF) tlast = clock64();
+            const long long tstart = tlast;
+            for (int st = cl_id; st < total_st; st += cl_n) {
+                const int nkb = p.cls[st_z(st)].ntaps * kb_per_tap;
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int s = g % STAGES;
+                    const uint32_t stage = smem_base + s * STAGE_BYTES;
+                    const int b = gc & 1;
+                    TC_PROF(3);
+                    mbar_wait(&full_bar[s], (uint32_t)((g / STAGES) & 1));
+                    TC_PROF(0);
+                    if (kb % CHUNK_KB == 0 && gc >= 2)      // buffer b must have been drained of chunk gc - 2
+                        mbar_wait(&drained_bar[b], (uint32_t)(((gc >> 1) - 1) & 1));
+                    TC_PROF(1);
+                    tc_fence_after();
+                    const uint64_t a_hi = make_desc(stage);
+                    const uint64_t a_lo = make_desc(stage + A_TILE_BYTES);
+                    const uint64_t b_hi = make_desc(stage + 2 * A_TILE_BYTES);
+                    const uint64_t b_lo = make_desc(stage + 2 * A_TILE_BYTES + B_TILE_BYTES);
+                    const uint32_t d_main = tmem_base + (uint32_t)(b * 2 * BN);
+                    const uint32_t d_cross = d_main + (uint32_t)BN;
+                    if (!(p.debug & 1))
 #pragma unroll
-                for (int ks = 0; ks < TBK / 8; ++ks) {
-                    const uint64_t adv = (uint64_t)(ks * 2);      // 32 bytes per k-step, in 16-byte units
-                    umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, ((kb % CHUNK_KB) | ks) != 0 ? 1u : 0u);
-                    umma_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
-                    umma_tf32(d_cross, a_hi + adv, b_lo + adv, idesc, 1u);
+                    for (int ks = 0; ks < TBK / 8; ++ks) {
+                        const uint64_t adv = (uint64_t)(ks * 2);      // 32 bytes per k-step, in 16-byte units
+                        const uint32_t accum = ((kb % CHUNK_KB) | ks) != 0 ? 1u : 0u;
+                        umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, accum);
+                        umma_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, accum);
+                        umma_tf32(d_cross, a_hi + adv, b_lo + adv, idesc, 1u);
+                    }
+                    umma_commit_mc(&empty_bar[s], cl_mask, CS > 1);
+                    if (kb % CHUNK_KB == CHUNK_KB - 1 || kb == nkb - 1) { umma_commit(&chunk_bar[b]); ++gc; }
+                    TC_PROF(2);
                 }
-                umma_commit(&empty_bar[s]);
-                if (kb % CHUNK_KB == CHUNK_KB - 1 || kb == nkb - 1) umma_commit(&chunk_bar[chunk & 1]);
-                if (kb == nkb - 1) umma_commit(&done_bar);
+            }
+            if constexpr (PROF) {
+                if (blockIdx.x == 0)
+                    printf("tcprof BN=%d N=%d C=%d quad=%d supertiles=%d cluster=%d kb/cta=%d | issuer total %lld: wait_full %lld wait_drained %lld issue %lld other %lld\n",
+                           BN, p.N, p.C, p.quad, total_st, CS, g, clock64() - tstart, prof[0], prof[1], prof[2], prof[3]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == kWeightWarp) {
+        // ================================ weight-tile producer ================================
+        // global layout (tc_weights_kernel): per tap 2*N*C floats; inside, block (n-tile y, k-block kc) holds the
+        // swizzled shared-memory image [hi: BN rows x 128 B | lo: BN rows x 128 B]
+        if (lane == 0) {
+            const uint32_t slice = (uint32_t)(2 * B_TILE_BYTES / CS);
+            int g = 0;
+            for (int st = cl_id; st < total_st; st += cl_n) {
+                const TapClass& cls = p.cls[st_z(st)];
+                const int y = st_y(st);
+                for (int tap = 0; tap < cls.ntaps; ++tap) {
+                    const float* wt = p.wk_hi + 2 * cls.taps[tap].w_off + (long long)y * kb_per_tap * (2 * BN * TBK);
+                    for (int kc = 0; kc < kb_per_tap; ++kc, ++g) {
+                        const int s = g % STAGES;
+                        if (g >= STAGES) mbar_wait(&empty_bar[s], (uint32_t)((g / STAGES - 1) & 1));
+                        if (!(p.debug & 8)) {
+                            mbar_expect_tx(&full_bar[s], (uint32_t)(2 * B_TILE_BYTES));
+                            const uint32_t dst = smem_base + s * STAGE_BYTES + 2 * A_TILE_BYTES + (uint32_t)rank * slice;
+                            const char* src = reinterpret_cast<const char*>(wt + (long long)kc * (2 * BN * TBK)) + (size_t)rank * slice;
+                            bulk_g2s(dst, src, slice, &full_bar[s], cl_mask, CS > 1);
+                        } else {
+                            mbar_arrive(&full_bar[s]);      // timing decomposition: no weight copy
+                        }
+                    }
+                }
             }
         }
         __syncwarp();
     } else {
-        // ================================ loaders / drain / epilogue ================================
-        // A rows: 8 threads cover the 128 bytes of one row, 32 rows per pass, 4 passes
+        // ================================ A loaders / drain / epilogue ================================
+        // The loader warps are INSTRUCTION bound (8 warps feed a 768-cycle MMA block per k-block), so the per-k-block
+        // code is kept minimal: 32-bit row offsets, a per-tile bitmask of the in-bounds taps instead of per-load
+        // bounds tests, incrementally updated cursors, no divisions outside the per-tile setup.
         const int a_chunk = tid & 7;
-        long long a_base[4];
-        int a_iy[4], a_ix[4];
-        bool a_ok[4];
-        uint32_t a_soff[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int r = (tid >> 3) + i * 32;
-            const long long m = m0 + r;
-            a_ok[i] = m < M;
-            const long long mm = a_ok[i] ? m : 0;
-            const int n = (int)(mm / HoWo);
-            const int rem = (int)(mm - (long long)n * HoWo);
-            const int oy = rem / Wo;
-            const int ox = rem - oy * Wo;
-            a_iy[i] = oy * p.sstride;
-            a_ix[i] = ox * p.sstride;
-            a_base[i] = (long long)n * p.src_img + ((long long)a_iy[i] * p.Ws + a_ix[i]) * p.src_pitch + a_chunk * 4;
-            a_soff[i] = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((a_chunk ^ (r & 7)) << 4));
-        }
-        auto load_a = [&](int tap_idx, int c0, float4* regs) {
-            const Tap& t = cls.taps[tap_idx];
+        // row r = tid/8 + 32*i lives at (r/8)*1024 + (r%8)*128 + ((chunk ^ r%8) * 16): i only moves the 1 KB group
+        const uint32_t a_soff0 = (uint32_t)((tid >> 6) * 1024 + ((tid >> 3) & 7) * 128 + ((a_chunk ^ ((tid >> 3) & 7)) << 4));
+
+        // ---- A cursor (runs 2 k-blocks ahead of the stores): 8 threads cover the 128 bytes of one row,
+        //      32 rows per pass, 4 passes
+        int stA = cl_id, tapA = 0, cA = 0;
+        int ntapsA = 0;
+        int offA = 0;                           // taps[tapA].src_off + cA: float offset added to the row bases
+        uint32_t tapbitA = 1u;
+        const TapClass* clsA = &p.cls[0];
+        uint32_t a_base[4];                     // float offset of the row's first tap position (< 2^31, checked at launch)
+        uint32_t a_taps[4];                     // bit t: tap t of this row is inside the source image (0: row beyond M)
+        auto setup_rows = [&]() {
+            clsA = &p.cls[st_z(stA)];
+            ntapsA = clsA->ntaps;
+            const int Wo = clsA->Wo, HoWo = clsA->Ho * Wo;
+            const long long M = (long long)p.batch * HoWo;
+            const long long m0 = st_m0(stA);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                bool v = a_ok[i];
-                if (p.check) v = v && (unsigned)(a_iy[i] + t.dy) < (unsigned)p.Hs && (unsigned)(a_ix[i] + t.dx) < (unsigned)p.Ws;
-                regs[i] = v ? __ldg(reinterpret_cast<const float4*>(p.src + a_base[i] + t.src_off + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const long long m = m0 + (tid >> 3) + i * 32;
+                const bool ok = m < M;
+                const long long mm = ok ? m : 0;
+                const int n = (int)(mm / HoWo);
+                const int rem = (int)(mm - (long long)n * HoWo);
+                const int oy = rem / Wo;
+                const int ox = rem - oy * Wo;
+                const int iy = oy * p.sstride, ix = ox * p.sstride;
+                a_base[i] = (uint32_t)((long long)n * p.src_img + ((long long)iy * p.Ws + ix) * p.src_pitch + a_chunk * 4);
+                uint32_t bits = 0xffffffffu;
+                if (p.check) {
+                    bits = 0u;
+                    for (int t = 0; t < ntapsA; ++t)
+                        if ((unsigned)(iy + clsA->taps[t].dy) < (unsigned)p.Hs && (unsigned)(ix + clsA->taps[t].dx) < (unsigned)p.Ws) bits |= 1u << t;
+                }
+                a_taps[i] = (ok && !(p.debug & 4)) ? bits : 0u;
             }
+            offA = (int)clsA->taps[0].src_off;
+            tapbitA = 1u;
         };
-        // B tiles (pre-split K-major weights): cp.async straight into the swizzled layout, one k-block ahead of A
-        int b_tap = 0, b_c = 0;
-        auto issue_b = [&](int kbt) {
-            const uint32_t stage = smem_base + (kbt % STAGES) * STAGE_BYTES;
-            const Tap& t = cls.taps[b_tap];
-            const long long woff = t.w_off + (long long)n0 * p.C + b_c;
+        if (stA < total_st) setup_rows();
+        auto load_a = [&](float4* regs) {       // loads the cursor's k-block (if any) and advances the cursor
+            if (stA >= total_st) return;
 #pragma unroll
-            for (int it = 0; it < B_ITERS; ++it) {
-                const int f = tid + it * 256;
-                if (B_CHUNKS % 256 == 0 || f < B_CHUNKS) {
-                    const int n = f >> 3, c = f & 7;
-                    const uint32_t so = (uint32_t)((n >> 3) * 1024 + (n & 7) * 128 + ((c ^ (n & 7)) << 4));
-                    const long long go = woff + (long long)n * p.C + c * 4;
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage + 2 * A_TILE_BYTES + so), "l"(p.wk_hi + go));
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage + 2 * A_TILE_BYTES + B_TILE_BYTES + so), "l"(p.wk_lo + go));
+            for (int i = 0; i < 4; ++i) {
+                regs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (a_taps[i] & tapbitA) regs[i] = __ldg(reinterpret_cast<const float4*>(p.src + (int)(a_base[i] + (uint32_t)offA)));
+            }
+            cA += TBK; offA += TBK;
+            if (cA == p.C) {
+                cA = 0;
+                if (++tapA == ntapsA) {
+                    tapA = 0;
+                    stA += cl_n;
+                    if (stA < total_st) setup_rows();
+                } else {
+                    offA = (int)clsA->taps[tapA].src_off;
+                    tapbitA <<= 1;
                 }
             }
-            b_c += TBK;
-            if (b_c == p.C) { b_c = 0; ++b_tap; }
         };
 
-        // register accumulators: this thread owns row (q*32 + lane) x columns [half*BN/2, +BN/2)
+        // ---- register accumulators: this thread owns row (q*32 + lane) x columns [half*BN/2, +BN/2) of the tile
+        //      being drained (stD)
         constexpr int HALF_COLS = BN / 2;
         const int q = warp & 3;                      // TMEM lane quarter this warp may access
         const int half = warp >> 2;                  // column half handled by this warp
@@ -183,91 +292,28 @@ tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
         float acc[HALF_COLS];
 #pragma unroll
         for (int i = 0; i < HALF_COLS; ++i) acc[i] = 0.f;
-        int drained = 0;
-        auto drain_one = [&]() {
-            const int b = drained & 1;
-            mbar_wait(&chunk_bar[b], (uint32_t)((drained >> 1) & 1));
-            tc_fence_after();
-#pragma unroll
-            for (int cc = 0; cc < HALF_COLS; cc += 16) {
-                float v[16];
-                tmem_ld16(tmem_lane + (uint32_t)(b * BN + cc), v);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) acc[cc + i] += v[i];
-            }
-            tc_fence_before();
-            mbar_arrive(&drained_bar[b]);
-            ++drained;
-        };
 
-        float4 areg[4];
-        int ld_tap = 0, ld_c = 0;
-        load_a(0, 0, areg);
-        issue_b(0);
-        cp_async_commit();
-
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t stage = smem_base + s * STAGE_BYTES;
-            // B(kb+1) into the next stage (free once the MMAs of k-block kb+1-STAGES retired); stage s itself was
-            // claimed the same way one iteration ago.
-            if (kb + 1 < nkb) {
-                if (kb + 1 >= STAGES) mbar_wait(&empty_bar[(kb + 1) % STAGES], (uint32_t)(((kb + 1) / STAGES - 1) & 1));
-                issue_b(kb + 1);
-            }
-            cp_async_commit();
-            // late drain: chunk j-2 retired long ago (the stage ring is no deeper than a chunk), never blocks
-            if (kb % CHUNK_KB == 0) {
-                while (drained < kb / CHUNK_KB - 1) drain_one();
-            }
-            // A tile: split the prefetched fp32 rows into hi / lo and store both (swizzled)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 x = areg[i];
-                float4 hi, lo;
-                split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y); split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
-                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage + a_soff[i]), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
-                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage + A_TILE_BYTES + a_soff[i]), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
-            }
-            // prefetch the next k-block's A rows
-            ld_c += TBK;
-            if (ld_c == p.C) { ld_c = 0; ++ld_tap; }
-            if (kb + 1 < nkb) load_a(ld_tap, ld_c, areg);
-
-            cp_async_wait<1>();          // everything but the group just committed: this thread's B(kb) chunks landed
-            fence_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
-            mbar_arrive(&full_bar[s]);
-        }
-
-        // drain what is still in TMEM (last one or two chunks, then the cross-term tile)
-        while (drained < nchunks) drain_one();
-        mbar_wait(&done_bar, 0);
-        tc_fence_after();
-#pragma unroll
-        for (int cc = 0; cc < HALF_COLS; cc += 16) {
-            float v[16];
-            tmem_ld16(tmem_lane + (uint32_t)(2 * BN + cc), v);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) acc[cc + i] += v[i];
-        }
-        // epilogue from registers: bias / ReLU / mask -> global
-        const int row = q * 32 + lane;
-        const long long m = m0 + row;
-        if (m < M) {
+        auto epilogue = [&](int st) {                // bias / ReLU / mask -> global, from the register accumulators
+            const TapClass& cls = p.cls[st_z(st)];
+            const int Wo = cls.Wo, HoWo = cls.Ho * Wo;
+            const long long m = st_m0(st) + q * 32 + lane;
+            if (m >= (long long)p.batch * HoWo) return;
             const int n = (int)(m / HoWo);
             const int rem = (int)(m - (long long)n * HoWo);
             const int oy = rem / Wo;
             const int ox = rem - oy * Wo;
-            const int col0 = n0 + half * HALF_COLS;
-            const long long img = (long long)n * p.dst_img;
-            const long long off_plain = img + ((long long)(oy * p.dstride + cls.py) * p.Wd + (ox * p.dstride + cls.px)) * p.dst_pitch;
+            const int col0 = st_y(st) * BN + half * HALF_COLS;
+            // destination float offsets fit 32 bits (checked at launch)
+            const uint32_t img = (uint32_t)n * (uint32_t)p.dst_img;
+            const uint32_t off_plain = img + (uint32_t)(((oy * p.dstride + cls.py) * p.Wd + (ox * p.dstride + cls.px)) * p.dst_pitch);
+            const int lcb = p.quad_lcb;              // log2(quad_cb)
             // groups of 4 columns, handled 4 at a time so that the ReLU-mask loads of a batch are all in flight
             // together (one at a time they serialise 16 global round trips per thread)
             constexpr int NG = HALF_COLS / 4;
             constexpr int GB = NG < 4 ? NG : 4;
 #pragma unroll
             for (int g0 = 0; g0 < NG; g0 += GB) {
-                long long offs[GB];
+                uint32_t offs[GB];
                 int chs[GB];
                 bool oks[GB];
                 float4 mks[GB];
@@ -276,14 +322,14 @@ tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
                     const int col = col0 + (g0 + u) * 4;
                     oks[u] = true;
                     if (p.quad) {
-                        const int c = col / p.quad_cb;
-                        chs[u] = col - c * p.quad_cb;
+                        const int c = col >> lcb;
+                        chs[u] = col & (p.quad_cb - 1);
                         const int y = oy * 2 + (c >> 1), x = ox * 2 + (c & 1);
                         oks[u] = y < p.Hd && x < p.Wd;
-                        offs[u] = img + ((long long)y * p.Wd + x) * p.dst_pitch + chs[u];
+                        offs[u] = img + (uint32_t)((y * p.Wd + x) * p.dst_pitch + chs[u]);
                     } else {
                         chs[u] = col;
-                        offs[u] = off_plain + col;
+                        offs[u] = off_plain + (uint32_t)col;
                     }
                 }
                 if (p.mask) {
@@ -308,35 +354,182 @@ tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
                     *reinterpret_cast<float4*>(p.dst + offs[u]) = o;
                 }
             }
+        };
+
+        // ---- drain cursor: chunk `drained` belongs to super-tile stD, which has chunksD chunks left
+        auto st_chunks = [&](int st) { return (p.cls[st_z(st)].ntaps * kb_per_tap + CHUNK_KB - 1) / CHUNK_KB; };
+        int drained = 0;
+        long long epi_cycles = 0;
+        int stD = cl_id;
+        int chunksD = stD < total_st ? st_chunks(stD) : 0;
+        auto drain_one = [&]() {
+            const int b = drained & 1;
+            mbar_wait(&chunk_bar[b], (uint32_t)((drained >> 1) & 1));
+            tc_fence_after();
+#pragma unroll
+            for (int cc = 0; cc < HALF_COLS; cc += 16) {
+                float v[16];
+                tmem_ld16(tmem_lane + (uint32_t)(b * 2 * BN + cc), v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[cc + i] += v[i];
+                tmem_ld16(tmem_lane + (uint32_t)(b * 2 * BN + BN + cc), v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[cc + i] += v[i];
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&drained_bar[b]);
+            ++drained;
+            if (--chunksD == 0) {
+                long long e0 = 0;
+                if constexpr (PROF) e0 = clock64();
+                epilogue(stD);
+                if constexpr (PROF) epi_cycles += clock64() - e0;
+#pragma unroll
+                for (int i = 0; i < HALF_COLS; ++i) acc[i] = 0.f;
+                stD += cl_n;
+                chunksD = stD < total_st ? st_chunks(stD) : 0;
+            }
+        };
+
+        // ---- store stream.  Two k-blocks of A rows are in flight per thread (register double buffer xa0 / xa1).
+        float4 xa0[4], xa1[4];
+        load_a(xa0);
+        load_a(xa1);
+        int g = 0, gc = 0;                          // k-blocks / chunks handed to the issuer so far
+        int sS = 0;                                 // stage of k-block g and the parity its empty barrier shows once free
+        uint32_t phS = 1;                           // (fresh barrier: the "previous" phase, parity 1, counts as complete)
+        long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
+        if constexpr (PROF) tlast = clock64();
+        const long long tstart = tlast;
+        auto step = [&](float4* xa) {
+            const uint32_t stage = smem_base + sS * STAGE_BYTES + a_soff0;
+            mbar_wait(&empty_bar[sS], phS);
+            TC_PROF(0);
+            // A tile: split the prefetched fp32 rows into hi / lo and store both (swizzled)
+            if (!(p.debug & 2))
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 x = xa[i];
+                float4 hi, lo;
+                split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y); split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage + i * 4096), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage + A_TILE_BYTES + i * 4096), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+            }
+            TC_PROF(3);
+            fence_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[sS]);
+            TC_PROF(6);
+            load_a(xa);                  // A rows of k-block g+2
+            TC_PROF(4);
+            ++g;
+            if (++sS == STAGES) { sS = 0; phS ^= 1u; }
+        };
+        // single loop over the k-block stream; ONE inlined copy of the drain + epilogue code
+        int st = cl_id, kb = 0;
+        int nkb = st < total_st ? p.cls[st_z(st)].ntaps * kb_per_tap : 0;
+        for (;;) {
+            const bool more = st < total_st;
+            // late drain: chunk gc-2 retired long ago (the stage ring is no deeper than a chunk); at the end, everything
+            const int target = more ? ((kb & (CHUNK_KB - 1)) == 0 ? gc - 1 : 0) : gc;
+            while (drained < target) drain_one();
+            TC_PROF(2);
+            if (!more) break;
+            if (g & 1) step(xa1); else step(xa0);
+            if ((kb & (CHUNK_KB - 1)) == CHUNK_KB - 1 || kb == nkb - 1) ++gc;
+            if (++kb == nkb) {
+                kb = 0;
+                st += cl_n;
+                if (st < total_st) nkb = p.cls[st_z(st)].ntaps * kb_per_tap;
+            }
+            TC_PROF(7);
+        }
+        if constexpr (PROF) {
+            if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 5))
+                printf("tcprof   loader warp %d total %lld: wait_empty %lld drain+epi %lld (epi %lld) split+sts %lld load_a %lld fence+arrive %lld loop %lld\n",
+                       warp, clock64() - tstart, prof[0], prof[2], epi_cycles, prof[3], prof[4], prof[6], prof[7]);
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (CS > 1) cluster_sync_all();             // nobody leaves while a peer may still multicast to / arrive on it
     if (warp == 0) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
-template <int BN>
-int32_t tc_launch(const TapGemmParams& p, cudaStream_t stream) {
-    using Cfg = TcCfg<BN>;
-    long long max_m = 0;
-    for (int c = 0; c < p.nclass; ++c) {
-        long long m = (long long)p.batch * p.cls[c].Ho * p.cls[c].Wo;
-        if (m > max_m) max_m = m;
-    }
-    if (max_m == 0) return CPB_OK;
-    dim3 grid((unsigned)((max_m + TBM - 1) / TBM), (unsigned)(p.N / BN), (unsigned)p.nclass);
-    tc_tapgemm_kernel<BN><<<grid, kTcThreads, Cfg::SMEM_BYTES, stream>>>(p);
+constexpr int tc_bn_slot(int BN) { return BN == 128 ? 2 : (BN == 64 ? 1 : 0); }
+
+template <int BN, bool PROF>
+int32_t tc_launch_t(const TapGemmParams& p, int mgroups, int total_st, unsigned grid, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = TcCfg<BN>::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = (unsigned)p.cluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    CPB_CUDA(cudaLaunchKernelEx(&cfg, tc_tapgemm_kernel<BN, PROF>, p, mgroups, total_st));
     CPB_LAUNCHED();
     return CPB_OK;
 }
 
 template <int BN>
+int32_t tc_launch(const TapGemmParams& p0, cudaStream_t stream) {
+    long long max_m = 0;
+    for (int c = 0; c < p0.nclass; ++c) {
+        long long m = (long long)p0.batch * p0.cls[c].Ho * p0.cls[c].Wo;
+        if (m > max_m) max_m = m;
+    }
+    if (max_m == 0) return CPB_OK;
+    TapGemmParams p = p0;
+    p.cluster = g_tc_cluster;
+    const long long mtiles = (max_m + TBM - 1) / TBM;
+    const long long mgroups = (mtiles + p.cluster - 1) / p.cluster;
+    const long long total_st = mgroups * (p.N / BN) * p.nclass;
+    const int resident = g_tc_clusters[tc_bn_slot(BN)];
+    CPB_REQUIRE(total_st < (1ll << 30) && resident > 0, "tc_tapgemm: bad tile count");
+    CPB_REQUIRE((long long)p.batch * p.src_img < (1ll << 31) && (long long)p.batch * p.dst_img < (1ll << 31),
+                "tc_tapgemm: tensors too large for 32-bit row offsets");
+    for (int c = 0; c < p.nclass; ++c) CPB_REQUIRE(p.cls[c].ntaps <= 32, "tc_tapgemm: more than 32 taps");
+    if (p.quad) {
+        CPB_REQUIRE((p.quad_cb & (p.quad_cb - 1)) == 0, "tc_tapgemm: quad form needs a power-of-two channel count");
+        p.quad_lcb = 0;
+        while ((1 << p.quad_lcb) < p.quad_cb) ++p.quad_lcb;
+    }
+    const unsigned grid = (unsigned)((total_st < resident ? total_st : resident) * p.cluster);
+    if (p.debug & 16) return tc_launch_t<BN, true>(p, (int)mgroups, (int)total_st, grid, stream);
+    return tc_launch_t<BN, false>(p, (int)mgroups, (int)total_st, grid, stream);
+}
+
+template <int BN>
 int32_t tc_init_one() {
-    CPB_CUDA(cudaFuncSetAttribute(tc_tapgemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES));
+    using Cfg = TcCfg<BN>;
+    CPB_CUDA(cudaFuncSetAttribute(tc_tapgemm_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    CPB_CUDA(cudaFuncSetAttribute(tc_tapgemm_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    // how many clusters of this kernel are co-resident (GPC boundaries can strand SMs for cluster sizes > 1)
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(g_tc_cluster * 1024));
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = (unsigned)g_tc_cluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    int n = 0;
+    CPB_CUDA(cudaOccupancyMaxActiveClusters(&n, tc_tapgemm_kernel<BN, false>, &cfg));
+    CPB_REQUIRE(n > 0, "tc_tapgemm: no resident cluster of %d CTAs possible", g_tc_cluster);
+    g_tc_clusters[tc_bn_slot(BN)] = n;
     return CPB_OK;
 }
 
-// weight preparation: per tap, a K-major [N][C] block, split into hi / lo
+// weight preparation.  Logical operand: per tap a K-major [N][C] matrix.  Stored per tap as 2*N*C floats: for each
+// (n-tile y of BN rows, k-block kc of 32 floats) one block [hi image | lo image], each image the BN x 128-byte
+// SWIZZLE_128B shared-memory tile exactly as the tensor core reads it -- so a k-block's operand is ONE contiguous
+// 2*BN*128-byte bulk copy (tc_tapgemm_kernel, weight-tile producer).
 __global__ void tc_weights_kernel(const float* __restrict__ params, float* __restrict__ dst, const __grid_constant__ TcWeightTable t) {
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= t.total) return;
@@ -344,37 +537,53 @@ __global__ void tc_weights_kernel(const float* __restrict__ params, float* __res
     while (j < t.njobs - 1 && idx >= t.jobs[j].count) { idx -= t.jobs[j].count; ++j; }
     const TcWeightJob& job = t.jobs[j];
     float x;
+    int tap, n, c;          // logical coordinates of element idx
     if (job.mode == 0) {
+        // plain K-major matrix [N][C], one tap
+        tap = 0; n = (int)(idx / job.C); c = (int)(idx % job.C);
         x = params[job.src_off + idx];
     } else if (job.mode == 2) {
-        // quad scatter form: destination [j][i][class*Cb + cb][cs]; class (py,px) uses kernel tap (py+2j, px+2i)
+        // quad scatter form: logical [j][i][class*Cb + cb][cs]; class (py,px) uses kernel tap (py+2j, px+2i)
         const int w = (job.k + 1) / 2;
         const int cs = (int)(idx % job.cs);
         long long rest = idx / job.cs;
         const int ncol = (int)(rest % (4 * job.cb));
         rest /= (4 * job.cb);
-        const int i = (int)(rest % w), j = (int)(rest / w);
+        const int i = (int)(rest % w), jj = (int)(rest / w);
         const int cls = ncol / job.cb, cb = ncol - cls * job.cb;
-        const int kh = (cls >> 1) + 2 * j, kw = (cls & 1) + 2 * i;
+        const int kh = (cls >> 1) + 2 * jj, kw = (cls & 1) + 2 * i;
         x = (kh < job.k && kw < job.k) ? params[job.src_off + (((long long)kh * job.k + kw) * job.cb + cb) * job.cs + cs] : 0.f;
+        tap = jj * w + i; n = ncol; c = cs;
     } else {
-        // gather form: destination [kh][cs][kw*Cb + cb]  <-  source [kh][kw][cb][cs]
+        // gather form: logical [kh][cs][kw*Cb + cb]  <-  source [kh][kw][cb][cs]
         const int run = job.k * job.cb;
-        const int c = (int)(idx % run);
+        const int cc = (int)(idx % run);
         const long long rest = idx / run;
         const int cs = (int)(rest % job.cs);
         const int kh = (int)(rest / job.cs);
-        const int kw = c / job.cb, cb = c - kw * job.cb;
+        const int kw = cc / job.cb, cb = cc - kw * job.cb;
         x = params[job.src_off + (((long long)kh * job.k + kw) * job.cb + cb) * job.cs + cs];
+        tap = kh; n = cs; c = cc;
     }
+    const int BN = tc_bn(job.N);
+    const int nn = n % BN, cc = c % TBK;
+    const long long block = ((long long)tap * (job.N / BN) + n / BN) * (job.C / TBK) + c / TBK;
+    const long long at = job.dst_hi + block * (2 * BN * TBK) + (nn >> 3) * 256 + (nn & 7) * 32 + ((((cc >> 2) ^ (nn & 7))) << 2) + (cc & 3);
     const float hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
-    dst[job.dst_hi + idx] = hi;
-    dst[job.dst_lo + idx] = x - hi;
+    dst[at] = hi;
+    dst[at + BN * TBK] = x - hi;
 }
 
 }  // namespace
 
 int32_t tc_tapgemm_init() {
+    int dev = 0, sms = 0;
+    CPB_CUDA(cudaGetDevice(&dev));
+    CPB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    (void)sms;
+    const char* e = getenv("CPB_TC_CLUSTER");
+    g_tc_cluster = e ? atoi(e) : 2;
+    CPB_REQUIRE(g_tc_cluster == 1 || g_tc_cluster == 2 || g_tc_cluster == 4 || g_tc_cluster == 8, "CPB_TC_CLUSTER must be 1, 2, 4 or 8");
     CPB_TRY(tc_init_one<32>());
     CPB_TRY(tc_init_one<64>());
     CPB_TRY(tc_init_one<128>());
@@ -388,9 +597,11 @@ bool tc_tapgemm_supported(const TapGemmParams& p) {
 
 int32_t launch_tc_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
     CPB_REQUIRE(tc_tapgemm_supported(p), "tc_tapgemm: unsupported problem (C=%d, N=%d)", p.C, p.N);
-    if (p.N % 128 == 0) return tc_launch<128>(p, stream);
-    if (p.N % 64 == 0) return tc_launch<64>(p, stream);
-    return tc_launch<32>(p, stream);
+    switch (tc_bn(p.N)) {
+        case 128: return tc_launch<128>(p, stream);
+        case 64: return tc_launch<64>(p, stream);
+        default: return tc_launch<32>(p, stream);
+    }
 }
 
 int32_t launch_tc_weights(const float* params, float* dst, const TcWeightTable& table, cudaStream_t stream) {

@@ -33,8 +33,11 @@ struct TcWgCfg {
     static constexpr int TMEM_COLS = BN == 128 ? 512 : (BN == 64 ? 256 : 128);
 };
 
+constexpr int kWgLoaderWarps = 8;
+constexpr int kWgThreads = kWgLoaderWarps * 32 + 32;      // + warp 8: MMA issuer (one elected lane)
+
 template <int BN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kWgThreads, 1)
 tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
     using Cfg = TcWgCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
@@ -43,8 +46,10 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
     static_assert(STAGES <= CHUNK_KB, "late drain relies on the stage ring being no deeper than a chunk");
 
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t empty_bar[STAGES];
-    __shared__ uint64_t chunk_bar[2];
+    __shared__ uint64_t full_bar[STAGES];     // loader warps -> issuer (one arrival per warp)
+    __shared__ uint64_t empty_bar[STAGES];    // tensor core -> loaders
+    __shared__ uint64_t chunk_bar[2];         // tensor core -> loaders: main tile b holds a finished chunk
+    __shared__ uint64_t drained_bar[2];       // loader warps -> issuer: main tile b was added to the registers
     __shared__ uint64_t done_bar;
     __shared__ uint32_t tmem_slot;
 
@@ -62,9 +67,11 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) mbar_init(&empty_bar[s], 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], kWgLoaderWarps); mbar_init(&empty_bar[s], 1); }
         mbar_init(&chunk_bar[0], 1);
         mbar_init(&chunk_bar[1], 1);
+        mbar_init(&drained_bar[0], kWgLoaderWarps);
+        mbar_init(&drained_bar[1], kWgLoaderWarps);
         mbar_init(&done_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -73,146 +80,164 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
+    const int nchunks = (nkb + CHUNK_KB - 1) / CHUNK_KB;
 
-    // ---- loader: thread = (channel group cg of 4 channels, position block mb of 4 reduction positions).
-    //      A quarter-warp = 8 consecutive channel groups of ONE position: its LDG.128 is one contiguous 128-byte
-    //      line (the L1 data pipe charges a wavefront per 32-byte sector when a quarter-warp straddles lines).
-    //      Conflict-free stores then need the 8 lanes to hit 8 different swizzle slots: channel 4*cg + c is kept in
-    //      tile row rho = 32*c + cg (A) / (BN/4)*c + cg (B), so a quarter-warp's rows differ in rho%8.  The
-    //      accumulator rows / columns come out permuted the same way and are un-permuted when the partial is stored.
-    const int cg = (warp & 3) * 8 + (lane & 7);
-    const int mb = (warp >> 2) * 4 + (lane >> 3);
-    const int a_i = i0 + cg * 4;
-    const bool a_col_ok = a_i < p.I;
-    long long a_coloff = 0;
-    if (a_col_ok) {
-        const int tap = a_i / p.run;
-        a_coloff = p.tap_off[tap] + (a_i - tap * p.run);
-    }
-    constexpr int BQ = BN / 4;                       // channel groups of the B tile
-    const bool b_col_ok = cg < BQ;
-    uint32_t soff[4], soffb[4];
+    if (warp == kWgLoaderWarps) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+            const uint32_t d_cross = tmem_base + (uint32_t)(2 * BN);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t stage = smem_base + s * STAGE_BYTES;
+                const int chunk = kb / CHUNK_KB;
+                mbar_wait(&full_bar[s], (uint32_t)((kb / STAGES) & 1));
+                if (kb % CHUNK_KB == 0 && chunk >= 2)
+                    mbar_wait(&drained_bar[chunk & 1], (uint32_t)(((chunk >> 1) - 1) & 1));
+                tc_fence_after();
+                const uint64_t a_hi = make_desc(stage);
+                const uint64_t a_lo = make_desc(stage + A_TILE_BYTES);
+                const uint64_t b_hi = make_desc(stage + 2 * A_TILE_BYTES);
+                const uint64_t b_lo = make_desc(stage + 2 * A_TILE_BYTES + B_TILE_BYTES);
+                const uint32_t d_main = tmem_base + (uint32_t)((chunk & 1) * BN);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const int ra = 32 * c + cg;
-        soff[c] = (uint32_t)((ra >> 3) * 1024 + (ra & 7) * 128 + ((mb ^ (ra & 7)) << 4));
-        const int rb = BQ * c + (cg % BQ);
-        soffb[c] = (uint32_t)((rb >> 3) * 1024 + (rb & 7) * 128 + ((mb ^ (rb & 7)) << 4));
-    }
-
-    float4 areg[4], breg[4];
-    auto load_regs = [&](int kb) {
-        long long m = m_begin + (long long)kb * TBK + mb * 4;
-        int n = 0, oy = 0, ox = 0;
-        if (m < m_end) {
-            n = (int)(m / HoWo);
-            const int rem = (int)(m - (long long)n * HoWo);
-            oy = rem / p.Wo;
-            ox = rem - oy * p.Wo;
+                for (int ks = 0; ks < TBK / 8; ++ks) {
+                    const uint64_t adv = (uint64_t)(ks * 2);          // 32 bytes per k-step (K-major)
+                    umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, ((kb % CHUNK_KB) | ks) != 0 ? 1u : 0u);
+                    umma_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
+                    umma_tf32(d_cross, a_hi + adv, b_lo + adv, idesc, 1u);
+                }
+                umma_commit(&empty_bar[s]);
+                if (kb % CHUNK_KB == CHUNK_KB - 1 || kb == nkb - 1) umma_commit(&chunk_bar[chunk & 1]);
+                if (kb == nkb - 1) umma_commit(&done_bar);
+            }
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const bool v = m + j < m_end;
-            const long long base = (long long)n * p.big_img + ((long long)(oy * p.sstride) * p.Wb + ox * p.sstride) * p.big_pitch;
-            areg[j] = (v && a_col_ok) ? __ldg(reinterpret_cast<const float4*>(p.big + base + a_coloff)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            breg[j] = (v && b_col_ok) ? __ldg(reinterpret_cast<const float4*>(p.small + (m + j) * p.J + j0 + cg * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (++ox == p.Wo) { ox = 0; if (++oy == p.Ho) { oy = 0; ++n; } }
+        __syncwarp();
+    } else {
+        // ================================ loaders / drain / partial store ================================
+        // thread = (channel group cg of 4 channels, position block mb of 4 reduction positions).
+        // A quarter-warp = 8 consecutive channel groups of ONE position: its LDG.128 is one contiguous 128-byte line
+        // (the L1 data pipe charges a wavefront per 32-byte sector when a quarter-warp straddles lines).
+        // Conflict-free stores then need the 8 lanes to hit 8 different swizzle slots: channel 4*cg + c is kept in
+        // tile row rho = 32*c + cg (A) / (BN/4)*c + cg (B), so a quarter-warp's rows differ in rho%8.  The
+        // accumulator rows / columns come out permuted the same way and are un-permuted when the partial is stored.
+        const int cg = (warp & 3) * 8 + (lane & 7);
+        const int mb = (warp >> 2) * 4 + (lane >> 3);
+        const int a_i = i0 + cg * 4;
+        const bool a_col_ok = a_i < p.I;
+        long long a_coloff = 0;
+        if (a_col_ok) {
+            const int tap = a_i / p.run;
+            a_coloff = p.tap_off[tap] + (a_i - tap * p.run);
         }
-    };
-
-    // 4x4 register transpose + split + store: x[j] = 4 channels at position j  ->  one chunk per channel
-    auto store_t = [&](uint32_t tile_hi, uint32_t tile_lo, const float4* x, const uint32_t* so) {
-        const float xs[4][4] = {{x[0].x, x[1].x, x[2].x, x[3].x}, {x[0].y, x[1].y, x[2].y, x[3].y},
-                                {x[0].z, x[1].z, x[2].z, x[3].z}, {x[0].w, x[1].w, x[2].w, x[3].w}};
+        constexpr int BQ = BN / 4;                       // channel groups of the B tile
+        const bool b_col_ok = cg < BQ;
+        uint32_t soff[4], soffb[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            float4 hi, lo;
-            split_tf32(xs[c][0], hi.x, lo.x); split_tf32(xs[c][1], hi.y, lo.y);
-            split_tf32(xs[c][2], hi.z, lo.z); split_tf32(xs[c][3], hi.w, lo.w);
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(tile_hi + so[c]), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(tile_lo + so[c]), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+            const int ra = 32 * c + cg;
+            soff[c] = (uint32_t)((ra >> 3) * 1024 + (ra & 7) * 128 + ((mb ^ (ra & 7)) << 4));
+            const int rb = BQ * c + (cg % BQ);
+            soffb[c] = (uint32_t)((rb >> 3) * 1024 + (rb & 7) * 128 + ((mb ^ (rb & 7)) << 4));
         }
-    };
 
-    constexpr int HALF_COLS = BN / 2;
-    const int q = warp & 3;
-    const int half = warp >> 2;
-    const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * HALF_COLS);
-    float acc[HALF_COLS];
-#pragma unroll
-    for (int i = 0; i < HALF_COLS; ++i) acc[i] = 0.f;
-    const int nchunks = (nkb + CHUNK_KB - 1) / CHUNK_KB;
-    int drained = 0;
-    auto drain_one = [&]() {
-        const int b = drained & 1;
-        mbar_wait(&chunk_bar[b], (uint32_t)((drained >> 1) & 1));
-        tc_fence_after();
-#pragma unroll
-        for (int cc = 0; cc < HALF_COLS; cc += 16) {
-            float v[16];
-            tmem_ld16(tmem_lane + (uint32_t)(b * BN + cc), v);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) acc[cc + i] += v[i];
-        }
-        tc_fence_before();
-        ++drained;
-    };
-
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
-    if (nkb > 0) load_regs(0);
-
-    for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t stage = smem_base + s * STAGE_BYTES;
-        if (kb >= STAGES) mbar_wait(&empty_bar[s], (uint32_t)((kb / STAGES - 1) & 1));
-        if (kb % CHUNK_KB == 0) {
-            while (drained < kb / CHUNK_KB - 1) drain_one();
-        }
-        store_t(stage, stage + A_TILE_BYTES, areg, soff);
-        if (b_col_ok) store_t(stage + 2 * A_TILE_BYTES, stage + 2 * A_TILE_BYTES + B_TILE_BYTES, breg, soffb);
-        if (kb + 1 < nkb) load_regs(kb + 1);
-
-        fence_async_smem();
-        __syncthreads();
-
-        if (tid == 0) {
-            tc_fence_after();
-            const uint64_t a_hi = make_desc(stage);
-            const uint64_t a_lo = make_desc(stage + A_TILE_BYTES);
-            const uint64_t b_hi = make_desc(stage + 2 * A_TILE_BYTES);
-            const uint64_t b_lo = make_desc(stage + 2 * A_TILE_BYTES + B_TILE_BYTES);
-            const int chunk = kb / CHUNK_KB;
-            const uint32_t d_main = tmem_base + (uint32_t)((chunk & 1) * BN);
-            const uint32_t d_cross = tmem_base + (uint32_t)(2 * BN);
-#pragma unroll
-            for (int ks = 0; ks < TBK / 8; ++ks) {
-                const uint64_t adva = (uint64_t)(ks * 2), advb = adva;          // 32 bytes per k-step (K-major)
-                umma_tf32(d_main, a_hi + adva, b_hi + advb, idesc, ((kb % CHUNK_KB) | ks) != 0 ? 1u : 0u);
-                umma_tf32(d_cross, a_lo + adva, b_hi + advb, idesc, (kb | ks) != 0 ? 1u : 0u);
-                umma_tf32(d_cross, a_hi + adva, b_lo + advb, idesc, 1u);
+        auto load_regs = [&](int kb, float4* areg, float4* breg) {
+            long long m = m_begin + (long long)kb * TBK + mb * 4;
+            int n = 0, oy = 0, ox = 0;
+            if (m < m_end) {
+                n = (int)(m / HoWo);
+                const int rem = (int)(m - (long long)n * HoWo);
+                oy = rem / p.Wo;
+                ox = rem - oy * p.Wo;
             }
-            umma_commit(&empty_bar[s]);
-            if (kb % CHUNK_KB == CHUNK_KB - 1 || kb == nkb - 1) umma_commit(&chunk_bar[chunk & 1]);
-            if (kb == nkb - 1) umma_commit(&done_bar);
-        }
-    }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool v = m + j < m_end;
+                const long long base = (long long)n * p.big_img + ((long long)(oy * p.sstride) * p.Wb + ox * p.sstride) * p.big_pitch;
+                areg[j] = (v && a_col_ok) ? __ldg(reinterpret_cast<const float4*>(p.big + base + a_coloff)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                breg[j] = (v && b_col_ok) ? __ldg(reinterpret_cast<const float4*>(p.small + (m + j) * p.J + j0 + cg * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (++ox == p.Wo) { ox = 0; if (++oy == p.Ho) { oy = 0; ++n; } }
+            }
+        };
 
-    if (nkb > 0) {
-        while (drained < nchunks) drain_one();
-        mbar_wait(&done_bar, 0);
-        tc_fence_after();
+        // 4x4 register transpose + split + store: x[j] = 4 channels at position j  ->  one chunk per channel
+        auto store_t = [&](uint32_t tile_hi, uint32_t tile_lo, const float4* x, const uint32_t* so) {
+            const float xs[4][4] = {{x[0].x, x[1].x, x[2].x, x[3].x}, {x[0].y, x[1].y, x[2].y, x[3].y},
+                                    {x[0].z, x[1].z, x[2].z, x[3].z}, {x[0].w, x[1].w, x[2].w, x[3].w}};
 #pragma unroll
-        for (int cc = 0; cc < HALF_COLS; cc += 16) {
-            float v[16];
-            tmem_ld16(tmem_lane + (uint32_t)(2 * BN + cc), v);
+            for (int c = 0; c < 4; ++c) {
+                float4 hi, lo;
+                split_tf32(xs[c][0], hi.x, lo.x); split_tf32(xs[c][1], hi.y, lo.y);
+                split_tf32(xs[c][2], hi.z, lo.z); split_tf32(xs[c][3], hi.w, lo.w);
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(tile_hi + so[c]), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(tile_lo + so[c]), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+            }
+        };
+
+        constexpr int HALF_COLS = BN / 2;
+        const int q = warp & 3;
+        const int half = warp >> 2;
+        const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * HALF_COLS);
+        float acc[HALF_COLS];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) acc[cc + i] += v[i];
+        for (int i = 0; i < HALF_COLS; ++i) acc[i] = 0.f;
+        int drained = 0;
+        auto drain_one = [&]() {
+            const int b = drained & 1;
+            mbar_wait(&chunk_bar[b], (uint32_t)((drained >> 1) & 1));
+            tc_fence_after();
+#pragma unroll
+            for (int cc = 0; cc < HALF_COLS; cc += 16) {
+                float v[16];
+                tmem_ld16(tmem_lane + (uint32_t)(b * BN + cc), v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[cc + i] += v[i];
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&drained_bar[b]);
+            ++drained;
+        };
+
+        // two k-blocks of operand rows are in flight per thread (register double buffer): with one, every
+        // k-block costs a full L2 round trip per warp
+        float4 xa0[4], xb0[4], xa1[4], xb1[4];
+        auto step = [&](int kb, float4* xa, float4* xb) {
+            const int s = kb % STAGES;
+            const uint32_t stage = smem_base + s * STAGE_BYTES;
+            if (kb >= STAGES) mbar_wait(&empty_bar[s], (uint32_t)((kb / STAGES - 1) & 1));
+            if (kb % CHUNK_KB == 0) {
+                while (drained < kb / CHUNK_KB - 1) drain_one();
+            }
+            store_t(stage, stage + A_TILE_BYTES, xa, soff);
+            if (b_col_ok) store_t(stage + 2 * A_TILE_BYTES, stage + 2 * A_TILE_BYTES + B_TILE_BYTES, xb, soffb);
+            if (kb + 2 < nkb) load_regs(kb + 2, xa, xb);
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[s]);
+        };
+        if (nkb > 0) load_regs(0, xa0, xb0);
+        if (nkb > 1) load_regs(1, xa1, xb1);
+        for (int kb = 0; kb < nkb; kb += 2) {
+            step(kb, xa0, xb0);
+            if (kb + 1 < nkb) step(kb + 1, xa1, xb1);
         }
-    }
-    // ---- partial[split][i][j]: TMEM lane rho = q*32 + lane holds channel i = 4*lane + q; accumulator column
-    //      rho_b = half*BN/2 + a holds j = 4*(rho_b % BQ) + rho_b / BQ, i.e. this thread has the column pairs
-    //      (4*cgb + 2*half, +1) for every cgb
-    {
+
+        if (nkb > 0) {
+            while (drained < nchunks) drain_one();
+            mbar_wait(&done_bar, 0);
+            tc_fence_after();
+#pragma unroll
+            for (int cc = 0; cc < HALF_COLS; cc += 16) {
+                float v[16];
+                tmem_ld16(tmem_lane + (uint32_t)(2 * BN + cc), v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[cc + i] += v[i];
+            }
+        }
+        // ---- partial[split][i][j]: TMEM lane rho = q*32 + lane holds channel i = 4*lane + q; accumulator column
+        //      rho_b = half*BN/2 + a holds j = 4*(rho_b % BQ) + rho_b / BQ, i.e. this thread has the column pairs
+        //      (4*cgb + 2*half, +1) for every cgb
         const int i = i0 + 4 * lane + q;
         if (i < p.I) {
             float* out = p.partial + ((long long)blockIdx.z * p.I + i) * p.J + j0 + 2 * half;
@@ -229,7 +254,7 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
 template <int BN>
 int32_t tc_wg_launch(const WgradParams& p, cudaStream_t stream) {
     dim3 grid((unsigned)cdiv(p.I, TBM), (unsigned)(p.J / BN), (unsigned)p.splits);
-    tc_wgrad_kernel<BN><<<grid, 256, TcWgCfg<BN>::SMEM_BYTES, stream>>>(p);
+    tc_wgrad_kernel<BN><<<grid, kWgThreads, TcWgCfg<BN>::SMEM_BYTES, stream>>>(p);
     CPB_LAUNCHED();
     return CPB_OK;
 }

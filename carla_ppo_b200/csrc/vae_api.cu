@@ -333,14 +333,23 @@ static TapGemmParams quad_from_scatter(const TapGemmParams& sp, int k) {
     return p;
 }
 
+// CPB_TC_DEBUG: timing decomposition of the tensor-core kernels (results are wrong when set; see tapgemm.cuh)
+static int tc_debug_flags() {
+    static const int v = [] { const char* e = getenv("CPB_TC_DEBUG"); return e ? atoi(e) : 0; }();
+    return v;
+}
+
 static int32_t tg(const char* label, const TapGemmParams& p, cudaStream_t s, int scatter_k = 0) {
     ProfScope prof(label, s);
     if (g_math_mode == 1) {
         if (scatter_k > 0 && p.wk_hi != nullptr) {
-            const TapGemmParams q = quad_from_scatter(p, scatter_k);
+            TapGemmParams q = quad_from_scatter(p, scatter_k);
+            q.debug = tc_debug_flags();
             if (tc_tapgemm_supported(q)) return launch_tc_tapgemm(q, s);
         } else if (tc_tapgemm_supported(p)) {
-            return launch_tc_tapgemm(p, s);
+            TapGemmParams q = p;
+            q.debug = tc_debug_flags();
+            return launch_tc_tapgemm(q, s);
         }
     }
     return launch_tapgemm(p, s);
@@ -361,6 +370,7 @@ static int32_t run_wgrad(const char* label, const float* big, int Wb, int pitch,
     if (g_math_mode == 1 && tc_wgrad_supported(w.I, w.J, w.run)) {
         w.splits = tc_wgrad_pick_splits(w.I, w.J, M);
         w.m_per_split = align_up((M + w.splits - 1) / w.splits, 32);
+        w.tc_variant = tc_debug_flags();
         CPB_TRY(launch_tc_wgrad(w, s));
     } else {
         w.splits = wgrad_pick_splits(w.I, w.J, M);
@@ -432,13 +442,13 @@ static int32_t relayout_weights(const VaePlan& pl, const VaeLayout& L, const flo
         if (gather) {
             TcWeightJob& j = w.jobs[w.njobs++];
             j.src_off = L.off[tensor]; j.dst_hi = pl.rl.tc[slot].f_hi; j.dst_lo = pl.rl.tc[slot].f_lo;
-            j.mode = 1; j.k = k; j.cb = cb; j.cs = cs; j.count = n; w.total += n;
+            j.mode = 1; j.k = k; j.cb = cb; j.cs = cs; j.N = cs; j.C = k * cb; j.count = n; w.total += n;
         }
         if (scatter) {
             TcWeightJob& j = w.jobs[w.njobs++];
             j.src_off = L.off[tensor]; j.dst_hi = pl.rl.tc[slot].t_hi; j.dst_lo = pl.rl.tc[slot].t_lo;
             const int win = (k + 1) / 2;
-            j.mode = 2; j.k = k; j.cb = cb; j.cs = cs; j.count = (long long)win * win * 4 * cb * cs; w.total += j.count;
+            j.mode = 2; j.k = k; j.cb = cb; j.cs = cs; j.N = 4 * cb; j.C = cs; j.count = (long long)win * win * 4 * cb * cs; w.total += j.count;
         }
     };
     // conv layers run gather-form forward / scatter-form dgrad; deconv layers the other way round
@@ -644,7 +654,7 @@ int32_t cpb_debug_tc_gemm(const float* a, const float* bt, float* d, int32_t m, 
     TcWeightTable w;
     memset(&w, 0, sizeof(w));
     w.njobs = 1; w.total = (long long)n * k;
-    w.jobs[0].src_off = 0; w.jobs[0].dst_hi = 0; w.jobs[0].dst_lo = (long long)n * k; w.jobs[0].mode = 0; w.jobs[0].count = w.total;
+    w.jobs[0].src_off = 0; w.jobs[0].dst_hi = 0; w.jobs[0].dst_lo = (long long)n * k; w.jobs[0].mode = 0; w.jobs[0].N = n; w.jobs[0].C = k; w.jobs[0].count = w.total;
     CPB_TRY(launch_tc_weights(bt, scratch, w, s));
     TapGemmParams p = dense_problem(a, m, k, nullptr, n, nullptr, nullptr, d, 0);
     p.wk_hi = scratch; p.wk_lo = scratch + (long long)n * k;
