@@ -37,7 +37,7 @@ struct TcCfg {
     static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
     static constexpr int STAGES = (STAGE_BYTES * 4 <= 200 * 1024) ? 4 : ((STAGE_BYTES * 3 <= 200 * 1024) ? 3 : 2);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;   // +1024: manual 1 KB alignment
-    static constexpr int TMEM_COLS = 4 * BN;                         // 2 x (main tile | cross tile): 512 / 256 / 128
+    static constexpr int TMEM_COLS = 4 * BN;                         // main0 | main1 (per chunk) | cross0 | cross1 (per tile): 512 / 256 / 128
 };
 constexpr int CHUNK_KB = 4;   // k-blocks accumulated inside TMEM before draining to registers (must be >= STAGES)
 
@@ -101,7 +101,7 @@ tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p, const int mgroups, co
     static_assert(STAGES <= CHUNK_KB, "late drain relies on the stage ring being no deeper than a chunk");
 
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t full_bar[STAGES];     // A loader warps + weight bytes -> issuer
+    __shared__ uint64_t full_bar[STAGES];     // A loader threads (cp.async completion) + weight bytes -> issuer
     __shared__ uint64_t empty_bar[STAGES];    // tensor cores of ALL CTAs of the cluster -> producers: stage is free everywhere
     __shared__ uint64_t chunk_bar[2];         // tensor core -> loaders: accumulator buffer b holds a finished chunk
     __shared__ uint64_t drained_bar[2];       // loader warps -> issuer: buffer b was added to the register accumulators
@@ -121,7 +121,7 @@ tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p, const int mgroups, co
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], kLoaderWarps + 1); mbar_init(&empty_bar[s], (uint32_t)CS); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], kLoaderWarps * 32 + 1); mbar_init(&empty_bar[s], (uint32_t)CS); }
         mbar_init(&chunk_bar[0], 1); mbar_init(&chunk_bar[1], 1);
         mbar_init(&drained_bar[0], kLoaderWarps); mbar_init(&drained_bar[1], kLoaderWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -147,7 +147,7 @@ tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p, const int mgroups, co
             long long prof[4] = {0, 0, 0, 0}, tlast = 0;
             if constexpr (PROF) tlast = clock64();
             const long long tstart = tlast;
-            for (int st = cl_id; st < total_st; st += cl_n) {
+            for (int st = cl_id, nt = 0; st < total_st; st += cl_n, ++nt) {
                 const int nkb = p.cls[st_z(st)].ntaps * kb_per_tap;
                 for (int kb = 0; kb < nkb; ++kb, ++g) {
                     const int s = g % STAGES;
@@ -159,20 +159,20 @@ tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p, const int mgroups, co
                     if (kb % CHUNK_KB == 0 && gc >= 2)      // buffer b must have been drained of chunk gc - 2
                         mbar_wait(&drained_bar[b], (uint32_t)(((gc >> 1) - 1) & 1));
                     TC_PROF(1);
+                    fence_async_smem();     // the A rows were written by cp.async (generic proxy); the MMA reads through the async proxy
                     tc_fence_after();
                     const uint64_t a_hi = make_desc(stage);
                     const uint64_t a_lo = make_desc(stage + A_TILE_BYTES);
                     const uint64_t b_hi = make_desc(stage + 2 * A_TILE_BYTES);
                     const uint64_t b_lo = make_desc(stage + 2 * A_TILE_BYTES + B_TILE_BYTES);
-                    const uint32_t d_main = tmem_base + (uint32_t)(b * 2 * BN);
-                    const uint32_t d_cross = d_main + (uint32_t)BN;
+                    const uint32_t d_main = tmem_base + (uint32_t)(b * BN);
+                    const uint32_t d_cross = tmem_base + (uint32_t)(2 * BN + (nt & 1) * BN);
                     if (!(p.debug & 1))
 #pragma unroll
                     for (int ks = 0; ks < TBK / 8; ++ks) {
                         const uint64_t adv = (uint64_t)(ks * 2);      // 32 bytes per k-step, in 16-byte units
-                        const uint32_t accum = ((kb % CHUNK_KB) | ks) != 0 ? 1u : 0u;
-                        umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, accum);
-                        umma_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, accum);
+                        umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, ((kb % CHUNK_KB) | ks) != 0 ? 1u : 0u);
+                        umma_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
                         umma_tf32(d_cross, a_hi + adv, b_lo + adv, idesc, 1u);
                     }
                     umma_commit_mc(&empty_bar[s], cl_mask, CS > 1);
@@ -217,15 +217,18 @@ tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p, const int mgroups, co
         __syncwarp();
     } else {
         // ================================ A loaders / drain / epilogue ================================
-        // The loader warps are INSTRUCTION bound (8 warps feed a 768-cycle MMA block per k-block), so the per-k-block
-        // code is kept minimal: 32-bit row offsets, a per-tile bitmask of the in-bounds taps instead of per-load
-        // bounds tests, incrementally updated cursors, no divisions outside the per-tile setup.
+        // The tensor core ignores the 13 low mantissa bits of a TF32 operand (scripts/diag_trunc.py: bit-identical
+        // results), so the raw fp32 activations ARE the "hi" operand; the "lo" operand (x - trunc(x)) comes from a
+        // plane written by lo_plane_kernel before this launch.  A tile rows are therefore copied global -> swizzled
+        // shared memory with cp.async (16 B per thread and row, zero-filled outside the image), completion is
+        // counted on the stage's mbarrier (cp.async.mbarrier.arrive.noinc) -- no registers, no split, no stores,
+        // no wait in the loader.  The loader warps are INSTRUCTION bound otherwise (8 warps feed a 768-cycle MMA
+        // block per k-block), which is why the per-k-block code is kept this small.
         const int a_chunk = tid & 7;
         // row r = tid/8 + 32*i lives at (r/8)*1024 + (r%8)*128 + ((chunk ^ r%8) * 16): i only moves the 1 KB group
         const uint32_t a_soff0 = (uint32_t)((tid >> 6) * 1024 + ((tid >> 3) & 7) * 128 + ((a_chunk ^ ((tid >> 3) & 7)) << 4));
 
-        // ---- A cursor (runs 2 k-blocks ahead of the stores): 8 threads cover the 128 bytes of one row,
-        //      32 rows per pass, 4 passes
+        // ---- A cursor: 8 threads cover the 128 bytes of one row, 32 rows per pass, 4 passes
         int stA = cl_id, tapA = 0, cA = 0;
         int ntapsA = 0;
         int offA = 0;                           // taps[tapA].src_off + cA: float offset added to the row bases
@@ -238,37 +241,44 @@ tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p, const int mgroups, co
             ntapsA = clsA->ntaps;
             const int Wo = clsA->Wo, HoWo = clsA->Ho * Wo;
             const long long M = (long long)p.batch * HoWo;
-            const long long m0 = st_m0(stA);
+            const uint32_t wo_magic = (uint32_t)((0x100000000ull + (uint32_t)Wo - 1) / (uint32_t)Wo);   // exact for rem < 65536
+            // first row by division, the other three are 32 positions apart
+            long long m = st_m0(stA) + (tid >> 3);
+            int n = (int)(m / HoWo);
+            int rem = (int)(m - (long long)n * HoWo);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const long long m = m0 + (tid >> 3) + i * 32;
                 const bool ok = m < M;
-                const long long mm = ok ? m : 0;
-                const int n = (int)(mm / HoWo);
-                const int rem = (int)(mm - (long long)n * HoWo);
-                const int oy = rem / Wo;
+                const int oy = (int)__umulhi((uint32_t)rem, wo_magic);
                 const int ox = rem - oy * Wo;
                 const int iy = oy * p.sstride, ix = ox * p.sstride;
-                a_base[i] = (uint32_t)((long long)n * p.src_img + ((long long)iy * p.Ws + ix) * p.src_pitch + a_chunk * 4);
+                a_base[i] = (uint32_t)n * (uint32_t)p.src_img + (uint32_t)((iy * p.Ws + ix) * p.src_pitch + a_chunk * 4);
                 uint32_t bits = 0xffffffffu;
                 if (p.check) {
                     bits = 0u;
                     for (int t = 0; t < ntapsA; ++t)
                         if ((unsigned)(iy + clsA->taps[t].dy) < (unsigned)p.Hs && (unsigned)(ix + clsA->taps[t].dx) < (unsigned)p.Ws) bits |= 1u << t;
                 }
-                a_taps[i] = (ok && !(p.debug & 4)) ? bits : 0u;
+                a_taps[i] = ok ? bits : 0u;
+                m += 32; rem += 32;
+                while (rem >= HoWo) { rem -= HoWo; ++n; }
             }
             offA = (int)clsA->taps[0].src_off;
             tapbitA = 1u;
         };
         if (stA < total_st) setup_rows();
-        auto load_a = [&](float4* regs) {       // loads the cursor's k-block (if any) and advances the cursor
-            if (stA >= total_st) return;
+        // copies the cursor's k-block into stage `stage` (hi = raw rows, lo = lo-plane rows) and advances the cursor
+        auto issue_a = [&](uint32_t stage, uint64_t* full) {
+            const uint32_t dst = stage + a_soff0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                regs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (a_taps[i] & tapbitA) regs[i] = __ldg(reinterpret_cast<const float4*>(p.src + (int)(a_base[i] + (uint32_t)offA)));
+                const bool v = (a_taps[i] & tapbitA) != 0u;
+                const uint32_t off = v ? a_base[i] + (uint32_t)offA : 0u;
+                const uint32_t bytes = v ? 16u : 0u;                 // 0: the 16 destination bytes are zero-filled
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + i * 4096), "l"(p.src + off), "r"(bytes) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + A_TILE_BYTES + i * 4096), "l"(p.src_lo + off), "r"(bytes) : "memory");
             }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(full)) : "memory");
             cA += TBK; offA += TBK;
             if (cA == p.C) {
                 cA = 0;
@@ -358,29 +368,42 @@ tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p, const int mgroups, co
 
         // ---- drain cursor: chunk `drained` belongs to super-tile stD, which has chunksD chunks left
         auto st_chunks = [&](int st) { return (p.cls[st_z(st)].ntaps * kb_per_tap + CHUNK_KB - 1) / CHUNK_KB; };
-        int drained = 0;
+        int drained = 0, ntD = 0;
         long long epi_cycles = 0;
+        // acc += 32 lanes x BN/2 columns of TMEM; two tcgen05.ld in flight per wait (a single one per round trip
+        // costs ~200 cycles each while the MMAs are running)
+        auto drain_cols = [&](uint32_t taddr) {
+#pragma unroll
+            for (int cc = 0; cc < HALF_COLS; cc += 32) {
+                if constexpr (HALF_COLS >= 32) {
+                    float v[16], w[16];
+                    tmem_ld16_issue(taddr + (uint32_t)cc, v);
+                    tmem_ld16_issue(taddr + (uint32_t)(cc + 16), w);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { acc[cc + i] += v[i]; acc[cc + 16 + i] += w[i]; }
+                } else {
+                    float v[16];
+                    tmem_ld16(taddr + (uint32_t)cc, v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) acc[cc + i] += v[i];
+                }
+            }
+        };
         int stD = cl_id;
         int chunksD = stD < total_st ? st_chunks(stD) : 0;
         auto drain_one = [&]() {
             const int b = drained & 1;
             mbar_wait(&chunk_bar[b], (uint32_t)((drained >> 1) & 1));
             tc_fence_after();
-#pragma unroll
-            for (int cc = 0; cc < HALF_COLS; cc += 16) {
-                float v[16];
-                tmem_ld16(tmem_lane + (uint32_t)(b * 2 * BN + cc), v);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) acc[cc + i] += v[i];
-                tmem_ld16(tmem_lane + (uint32_t)(b * 2 * BN + BN + cc), v);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) acc[cc + i] += v[i];
-            }
+            drain_cols(tmem_lane + (uint32_t)(b * BN));
+            if (chunksD == 1) drain_cols(tmem_lane + (uint32_t)(2 * BN + (ntD & 1) * BN));   // last chunk of the tile: + its cross-term tile
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&drained_bar[b]);
             ++drained;
             if (--chunksD == 0) {
+                ++ntD;
                 long long e0 = 0;
                 if constexpr (PROF) e0 = clock64();
                 epilogue(stD);
@@ -392,40 +415,13 @@ tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p, const int mgroups, co
             }
         };
 
-        // ---- store stream.  Two k-blocks of A rows are in flight per thread (register double buffer xa0 / xa1).
-        float4 xa0[4], xa1[4];
-        load_a(xa0);
-        load_a(xa1);
-        int g = 0, gc = 0;                          // k-blocks / chunks handed to the issuer so far
-        int sS = 0;                                 // stage of k-block g and the parity its empty barrier shows once free
-        uint32_t phS = 1;                           // (fresh barrier: the "previous" phase, parity 1, counts as complete)
+        // ---- copy stream: the loaders run ahead of the tensor core by as many k-blocks as there are free stages
+        int gc = 0;                                 // chunks handed to the issuer so far
+        int sS = 0;                                 // stage of the next k-block and the parity its empty barrier
+        uint32_t phS = 1;                           // shows once free (fresh barrier: parity 1 counts as complete)
         long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
         if constexpr (PROF) tlast = clock64();
         const long long tstart = tlast;
-        auto step = [&](float4* xa) {
-            const uint32_t stage = smem_base + sS * STAGE_BYTES + a_soff0;
-            mbar_wait(&empty_bar[sS], phS);
-            TC_PROF(0);
-            // A tile: split the prefetched fp32 rows into hi / lo and store both (swizzled)
-            if (!(p.debug & 2))
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 x = xa[i];
-                float4 hi, lo;
-                split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y); split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
-                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage + i * 4096), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
-                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage + A_TILE_BYTES + i * 4096), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
-            }
-            TC_PROF(3);
-            fence_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full_bar[sS]);
-            TC_PROF(6);
-            load_a(xa);                  // A rows of k-block g+2
-            TC_PROF(4);
-            ++g;
-            if (++sS == STAGES) { sS = 0; phS ^= 1u; }
-        };
         // single loop over the k-block stream; ONE inlined copy of the drain + epilogue code
         int st = cl_id, kb = 0;
         int nkb = st < total_st ? p.cls[st_z(st)].ntaps * kb_per_tap : 0;
@@ -436,7 +432,11 @@ tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p, const int mgroups, co
             while (drained < target) drain_one();
             TC_PROF(2);
             if (!more) break;
-            if (g & 1) step(xa1); else step(xa0);
+            mbar_wait(&empty_bar[sS], phS);
+            TC_PROF(0);
+            issue_a(smem_base + sS * STAGE_BYTES, &full_bar[sS]);
+            TC_PROF(4);
+            if (++sS == STAGES) { sS = 0; phS ^= 1u; }
             if ((kb & (CHUNK_KB - 1)) == CHUNK_KB - 1 || kb == nkb - 1) ++gc;
             if (++kb == nkb) {
                 kb = 0;
@@ -447,8 +447,8 @@ tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p, const int mgroups, co
         }
         if constexpr (PROF) {
             if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 5))
-                printf("tcprof   loader warp %d total %lld: wait_empty %lld drain+epi %lld (epi %lld) split+sts %lld load_a %lld fence+arrive %lld loop %lld\n",
-                       warp, clock64() - tstart, prof[0], prof[2], epi_cycles, prof[3], prof[4], prof[6], prof[7]);
+                printf("tcprof   loader warp %d total %lld: wait_empty %lld drain+epi %lld (epi %lld) issue_a %lld loop %lld\n",
+                       warp, clock64() - tstart, prof[0], prof[2], epi_cycles, prof[4], prof[7]);
         }
     }
     tc_fence_before();
@@ -526,6 +526,16 @@ int32_t tc_init_one() {
     return CPB_OK;
 }
 
+// lo[i] = x[i] - trunc_tf32(x[i]): the second TF32 operand of an activation tensor (the first is x itself)
+__global__ void lo_plane_kernel(const float4* __restrict__ x, float4* __restrict__ lo, long long n4) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(x + i);
+        float4 h, l;
+        split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+        lo[i] = l;
+    }
+}
+
 // weight preparation.  Logical operand: per tap a K-major [N][C] matrix.  Stored per tap as 2*N*C floats: for each
 // (n-tile y of BN rows, k-block kc of 32 floats) one block [hi image | lo image], each image the BN x 128-byte
 // SWIZZLE_128B shared-memory tile exactly as the tensor core reads it -- so a k-block's operand is ONE contiguous
@@ -592,7 +602,7 @@ int32_t tc_tapgemm_init() {
 
 bool tc_tapgemm_supported(const TapGemmParams& p) {
     if (p.quad && (p.N != 4 * p.quad_cb || p.nclass != 1)) return false;
-    return p.ybatch == 1 && p.C % TBK == 0 && (p.N == 32 || p.N % 64 == 0) && p.wk_hi != nullptr && p.wk_lo != nullptr;
+    return p.ybatch == 1 && p.C % TBK == 0 && (p.N == 32 || p.N % 64 == 0) && p.wk_hi != nullptr && p.wk_lo != nullptr && p.src_lo != nullptr;
 }
 
 int32_t launch_tc_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
@@ -602,6 +612,16 @@ int32_t launch_tc_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
         case 64: return tc_launch<64>(p, stream);
         default: return tc_launch<32>(p, stream);
     }
+}
+
+int32_t launch_lo_plane(const float* x, float* lo, long long count, cudaStream_t stream) {
+    CPB_REQUIRE(count % 4 == 0, "lo_plane: count must be a multiple of 4");
+    if (count == 0) return CPB_OK;
+    const long long n4 = count / 4;
+    const long long want = (n4 + 255) / 256;
+    lo_plane_kernel<<<(unsigned)(want < 148 * 16 ? want : 148 * 16), 256, 0, stream>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(lo), n4);
+    CPB_LAUNCHED();
+    return CPB_OK;
 }
 
 int32_t launch_tc_weights(const float* params, float* dst, const TcWeightTable& table, cudaStream_t stream) {

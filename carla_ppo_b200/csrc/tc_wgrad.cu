@@ -141,23 +141,38 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
             soffb[c] = (uint32_t)((rb >> 3) * 1024 + (rb & 7) * 128 + ((mb ^ (rb & 7)) << 4));
         }
 
-        auto load_regs = [&](int kb, float4* areg, float4* breg) {
-            long long m = m_begin + (long long)kb * TBK + mb * 4;
-            int n = 0, oy = 0, ox = 0;
-            if (m < m_end) {
-                n = (int)(m / HoWo);
-                const int rem = (int)(m - (long long)n * HoWo);
-                oy = rem / p.Wo;
-                ox = rem - oy * p.Wo;
-            }
+        // position cursor of this thread's NEXT load (k-block kbL): image n, position rem = oy*Wo + ox inside it.
+        // Advancing by a k-block (32 positions) needs no division: oy comes from a multiply-high by ceil(2^32 / Wo).
+        const int len = (int)(m_end - m_begin);                    // reduction positions of this split
+        const uint32_t wo_magic = (uint32_t)((0x100000000ull + (uint32_t)p.Wo - 1) / (uint32_t)p.Wo);
+        const int dx = p.sstride * p.big_pitch;                              // next position in the row
+        const int drow = (p.sstride * p.Wb - p.Wo * p.sstride) * p.big_pitch;   // ... wrapping to the next row
+        const int dimg = (int)(p.big_img - (long long)p.Ho * p.sstride * p.Wb * p.big_pitch);   // ... to the next image
+        int nL, remL, relL = mb * 4;                               // relL: position index relative to m_begin
+        {
+            const long long m = m_begin + relL;
+            nL = (int)(m / HoWo);
+            remL = (int)(m - (long long)nL * HoWo);
+        }
+        const float* bptr = p.small + (m_begin + relL) * p.J + j0 + cg * 4;
+        auto load_regs = [&](float4* areg, float4* breg) {
+            int oy = (int)__umulhi((uint32_t)remL, wo_magic);
+            int ox = remL - oy * p.Wo;
+            uint32_t off = (uint32_t)nL * (uint32_t)p.big_img + (uint32_t)((oy * p.sstride * p.Wb + ox * p.sstride) * p.big_pitch) + (uint32_t)a_coloff;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const bool v = m + j < m_end;
-                const long long base = (long long)n * p.big_img + ((long long)(oy * p.sstride) * p.Wb + ox * p.sstride) * p.big_pitch;
-                areg[j] = (v && a_col_ok) ? __ldg(reinterpret_cast<const float4*>(p.big + base + a_coloff)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                breg[j] = (v && b_col_ok) ? __ldg(reinterpret_cast<const float4*>(p.small + (m + j) * p.J + j0 + cg * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                if (++ox == p.Wo) { ox = 0; if (++oy == p.Ho) { oy = 0; ++n; } }
+                const bool v = relL + j < len;
+                areg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                breg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (v && a_col_ok) areg[j] = __ldg(reinterpret_cast<const float4*>(p.big + off));
+                if (v && b_col_ok) breg[j] = __ldg(reinterpret_cast<const float4*>(bptr + j * p.J));
+                off += (uint32_t)dx;
+                if (++ox == p.Wo) { ox = 0; off += (uint32_t)drow; if (++oy == p.Ho) { oy = 0; off += (uint32_t)dimg; } }
             }
+            relL += TBK;
+            bptr += TBK * p.J;
+            remL += TBK;
+            while (remL >= HoWo) { remL -= HoWo; ++nL; }
         };
 
         // 4x4 register transpose + split + store: x[j] = 4 channels at position j  ->  one chunk per channel
@@ -182,17 +197,30 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
 #pragma unroll
         for (int i = 0; i < HALF_COLS; ++i) acc[i] = 0.f;
         int drained = 0;
+        // acc += 32 lanes x BN/2 columns of TMEM, two tcgen05.ld in flight per wait
+        auto drain_cols = [&](uint32_t taddr) {
+#pragma unroll
+            for (int cc = 0; cc < HALF_COLS; cc += 32) {
+                if constexpr (HALF_COLS >= 32) {
+                    float v[16], w[16];
+                    tmem_ld16_issue(taddr + (uint32_t)cc, v);
+                    tmem_ld16_issue(taddr + (uint32_t)(cc + 16), w);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { acc[cc + i] += v[i]; acc[cc + 16 + i] += w[i]; }
+                } else {
+                    float v[16];
+                    tmem_ld16(taddr + (uint32_t)cc, v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) acc[cc + i] += v[i];
+                }
+            }
+        };
         auto drain_one = [&]() {
             const int b = drained & 1;
             mbar_wait(&chunk_bar[b], (uint32_t)((drained >> 1) & 1));
             tc_fence_after();
-#pragma unroll
-            for (int cc = 0; cc < HALF_COLS; cc += 16) {
-                float v[16];
-                tmem_ld16(tmem_lane + (uint32_t)(b * BN + cc), v);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) acc[cc + i] += v[i];
-            }
+            drain_cols(tmem_lane + (uint32_t)(b * BN));
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&drained_bar[b]);
@@ -202,22 +230,24 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
         // two k-blocks of operand rows are in flight per thread (register double buffer): with one, every
         // k-block costs a full L2 round trip per warp
         float4 xa0[4], xb0[4], xa1[4], xb1[4];
+        int sS = 0;                                 // stage of the k-block being stored and the parity its empty
+        uint32_t phS = 1;                           // barrier shows once free (fresh barrier: parity 1 counts as complete)
         auto step = [&](int kb, float4* xa, float4* xb) {
-            const int s = kb % STAGES;
-            const uint32_t stage = smem_base + s * STAGE_BYTES;
-            if (kb >= STAGES) mbar_wait(&empty_bar[s], (uint32_t)((kb / STAGES - 1) & 1));
-            if (kb % CHUNK_KB == 0) {
+            const uint32_t stage = smem_base + sS * STAGE_BYTES;
+            mbar_wait(&empty_bar[sS], phS);
+            if ((kb & (CHUNK_KB - 1)) == 0) {
                 while (drained < kb / CHUNK_KB - 1) drain_one();
             }
             store_t(stage, stage + A_TILE_BYTES, xa, soff);
             if (b_col_ok) store_t(stage + 2 * A_TILE_BYTES, stage + 2 * A_TILE_BYTES + B_TILE_BYTES, xb, soffb);
-            if (kb + 2 < nkb) load_regs(kb + 2, xa, xb);
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&full_bar[s]);
+            if (lane == 0) mbar_arrive(&full_bar[sS]);
+            if (kb + 2 < nkb) load_regs(xa, xb);
+            if (++sS == STAGES) { sS = 0; phS ^= 1u; }
         };
-        if (nkb > 0) load_regs(0, xa0, xb0);
-        if (nkb > 1) load_regs(1, xa1, xb1);
+        if (nkb > 0) load_regs(xa0, xb0);
+        if (nkb > 1) load_regs(xa1, xb1);
         for (int kb = 0; kb < nkb; kb += 2) {
             step(kb, xa0, xb0);
             if (kb + 1 < nkb) step(kb + 1, xa1, xb1);
@@ -227,13 +257,7 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
             while (drained < nchunks) drain_one();
             mbar_wait(&done_bar, 0);
             tc_fence_after();
-#pragma unroll
-            for (int cc = 0; cc < HALF_COLS; cc += 16) {
-                float v[16];
-                tmem_ld16(tmem_lane + (uint32_t)(2 * BN + cc), v);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) acc[cc + i] += v[i];
-            }
+            drain_cols(tmem_lane + (uint32_t)(2 * BN));
         }
         // ---- partial[split][i][j]: TMEM lane rho = q*32 + lane holds channel i = 4*lane + q; accumulator column
         //      rho_b = half*BN/2 + a holds j = 4*(rho_b % BQ) + rho_b / BQ, i.e. this thread has the column pairs
@@ -290,6 +314,8 @@ int tc_wgrad_pick_splits(int I, int J, long long M) {
 int32_t launch_tc_wgrad(const WgradParams& p, cudaStream_t stream) {
     CPB_REQUIRE(tc_wgrad_supported(p.I, p.J, p.run) && p.I == p.ntaps * p.run, "tc_wgrad: unsupported problem (I=%d J=%d)", p.I, p.J);
     CPB_REQUIRE(p.m_per_split % TBK == 0 && p.splits >= 1, "tc_wgrad: bad split");
+    CPB_REQUIRE((long long)p.batch * p.big_img < (1ll << 31) && p.m_per_split < (1ll << 30) && p.Wo < 65536 && p.Ho * p.Wo < 65536,
+                "tc_wgrad: tensor too large for 32-bit offsets");
     switch (tc_wg_bn(p.J)) {
         case 128: return tc_wg_launch<128>(p, stream);
         case 64: return tc_wg_launch<64>(p, stream);

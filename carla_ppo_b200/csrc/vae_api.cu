@@ -170,6 +170,7 @@ struct VaePlan {
     float *relayout, *xp, *yp, *a1, *a2, *a3, *a4, *heads, *zbuf, *kl_rows, *kl_active, *frame_loss;
     float *d1, *b1, *b2, *b3, *logits_p;
     float *gA, *gB, *gz, *gheads, *partial, *colsum;
+    float* lo;          // lo plane scratch of the tensor-core tap-GEMM sources (largest: [B,39,79,32])
     int64_t bytes;
     bool ok;
 };
@@ -211,6 +212,7 @@ static VaePlan make_plan(void* ws, int64_t ws_bytes, int B, int ct, int z, int m
     p.a3 = a.take<float>(b * H3 * W3 * C3);
     p.a4 = a.take<float>(b * FEAT);
     p.heads = a.take<float>(2 * b * z);
+    p.lo = a.take<float>(b * H1 * W1 * C1);
     if (mode >= CPB_WS_FORWARD) {
         p.yp = a.take<float>(b * NPIX * 4);
         p.zbuf = a.take<float>(b * z);
@@ -339,16 +341,16 @@ static int tc_debug_flags() {
     return v;
 }
 
+static thread_local float* tl_lo_scratch = nullptr;   // lo plane of the current tensor-core source (VaePlan::lo)
+
 static int32_t tg(const char* label, const TapGemmParams& p, cudaStream_t s, int scatter_k = 0) {
     ProfScope prof(label, s);
-    if (g_math_mode == 1) {
-        if (scatter_k > 0 && p.wk_hi != nullptr) {
-            TapGemmParams q = quad_from_scatter(p, scatter_k);
-            q.debug = tc_debug_flags();
-            if (tc_tapgemm_supported(q)) return launch_tc_tapgemm(q, s);
-        } else if (tc_tapgemm_supported(p)) {
-            TapGemmParams q = p;
-            q.debug = tc_debug_flags();
+    if (g_math_mode == 1 && p.wk_hi != nullptr && tl_lo_scratch != nullptr) {
+        TapGemmParams q = scatter_k > 0 ? quad_from_scatter(p, scatter_k) : p;
+        q.debug = tc_debug_flags();
+        q.src_lo = tl_lo_scratch;
+        if (tc_tapgemm_supported(q)) {
+            CPB_TRY(launch_lo_plane(q.src, tl_lo_scratch, (long long)q.batch * q.src_img, s));
             return launch_tc_tapgemm(q, s);
         }
     }
@@ -465,6 +467,7 @@ static int32_t relayout_weights(const VaePlan& pl, const VaeLayout& L, const flo
 
 static int32_t run_encoder(const VaePlan& pl, const VaeLayout& L, const cpb_vae_config* cfg, const float* params,
                            const void* source, int32_t* flags, cudaStream_t s) {
+    tl_lo_scratch = pl.lo;
     using namespace geo;
     const int B = pl.B;
     const float sscale = cfg->source_dtype == CPB_FRAME_U8 ? 1.f / 255.f : 1.f;
@@ -494,6 +497,7 @@ static int32_t run_encoder(const VaePlan& pl, const VaeLayout& L, const cpb_vae_
 // zbuf -> d1 -> b1 -> b2 -> b3 -> (logits_p and/or sigmoid)
 static int32_t run_decoder(const VaePlan& pl, const VaeLayout& L, const float* params, const float* zsrc,
                            float* logits_p, float* sigm, cudaStream_t s) {
+    tl_lo_scratch = pl.lo;
     using namespace geo;
     const int B = pl.B;
     TapGemmParams p = dense_problem(zsrc, B, pl.z, params + L.off[T_DENSE1_K], FEAT, params + L.off[T_DENSE1_B],
@@ -539,6 +543,7 @@ static int32_t run_forward_loss(const VaePlan& pl, const VaeLayout& L, const cpb
 
 static int32_t run_backward(const VaePlan& pl, const VaeLayout& L, const cpb_vae_config* cfg, const float* params,
                             const float* eps, float* grads, cudaStream_t s) {
+    tl_lo_scratch = pl.lo;
     using namespace geo;
     const int B = pl.B;
     const int z = pl.z;
@@ -647,7 +652,7 @@ int32_t cpb_debug_vae_buffer_offsets(int32_t batch, int32_t ct, int32_t z, int32
     return n;
 }
 
-/* debug: D[M,N] = A[M,K] * Bt[N,K]^T through the tensor-core tap-GEMM (dense, one tap).  scratch: 2*N*K floats. */
+/* debug: D[M,N] = A[M,K] * Bt[N,K]^T through the tensor-core tap-GEMM (dense, one tap).  scratch: 2*N*K + M*K floats. */
 int32_t cpb_debug_tc_gemm(const float* a, const float* bt, float* d, int32_t m, int32_t n, int32_t k, float* scratch, void* stream) {
     CPB_TRY(ensure_init());
     cudaStream_t s = (cudaStream_t)stream;
@@ -658,6 +663,10 @@ int32_t cpb_debug_tc_gemm(const float* a, const float* bt, float* d, int32_t m, 
     CPB_TRY(launch_tc_weights(bt, scratch, w, s));
     TapGemmParams p = dense_problem(a, m, k, nullptr, n, nullptr, nullptr, d, 0);
     p.wk_hi = scratch; p.wk_lo = scratch + (long long)n * k;
+    p.debug = tc_debug_flags();
+    float* lo = scratch + 2LL * n * k;
+    p.src_lo = lo;
+    CPB_TRY(launch_lo_plane(a, lo, (long long)m * k, s));
     return launch_tc_tapgemm(p, s);
 }
 

@@ -1,4 +1,6 @@
 for cs in 1 2; do
+echo "=== cluster $cs"
+CPB_TC_CLUSTER=$cs timeout 200 python scripts/diag_tc.py 2>&1 | grep -v "^  [a-z]" | tail -12
 CPB_TC_CLUSTER=$cs timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bc$cs.json 2>gpurun_out/bc$cs.err
 python - <<PY
 import json
@@ -10,5 +12,4 @@ except Exception as e:
     print("CS $cs failed", e); print(open("gpurun_out/bc$cs.err").read()[-1500:])
 PY
 done
-CPB_TC_CLUSTER=1 timeout 300 python scripts/tc_prof.py 2>&1 | sed -n '/=== step 2/,$p' | grep -A2 "C=64 quad=1" | head -3 | cut -c1-300
 CPB_TC_CLUSTER=2 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3

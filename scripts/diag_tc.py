@@ -10,7 +10,7 @@ lib = _lib.load()
 def gemm(a, bt):
     m, k = a.shape; n = bt.shape[0]
     ta = torch.tensor(a, device="cuda"); tb = torch.tensor(bt, device="cuda")
-    d = torch.empty(m, n, device="cuda"); sc = torch.empty(2 * n * k, device="cuda")
+    d = torch.empty(m, n, device="cuda"); sc = torch.empty(2 * n * k + m * k, device="cuda")
     _lib.check(lib.cpb_debug_tc_gemm(ta.data_ptr(), tb.data_ptr(), d.data_ptr(), m, n, k, sc.data_ptr(), _lib.current_stream_handle()))
     torch.cuda.synchronize()
     return d.cpu().numpy()
