@@ -65,7 +65,7 @@ struct TapGemmParams {
     int quad_cb;
     int quad_lcb;         // log2(quad_cb), set by the launcher
     int cluster;          // tensor-core path: CTAs per cluster (set by the launcher)
-    int debug;            // tensor-core path: timing decomposition (CPB_TC_DEBUG): 1 no MMA, 2 no A stores, 4 no A loads, 8 no B copies
+    int debug;            // tensor-core path: timing decomposition (CPB_TC_DEBUG): 1 no MMA, 2 no A copies, 4 A copies zero-fill only, 8 no weight copies, 16 cycle accounting
     TapClass cls[4];
 };
 

@@ -37,14 +37,17 @@ struct TcCfg {
     static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
     static constexpr int STAGES = (STAGE_BYTES * 4 <= 200 * 1024) ? 4 : ((STAGE_BYTES * 3 <= 200 * 1024) ? 3 : 2);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;   // +1024: manual 1 KB alignment
-    static constexpr int TMEM_COLS = 4 * BN;                         // main0 | main1 (per chunk) | cross0 | cross1 (per tile): 512 / 256 / 128
+    static constexpr int TMEM_COLS = 4 * BN;                         // 2 chunk buffers x (main | cross): 512 / 256 / 128
 };
 constexpr int CHUNK_KB = 4;   // k-blocks accumulated inside TMEM before draining to registers (must be >= STAGES)
 
-constexpr int kLoaderWarps = 8;                       // warps 0-7: A loaders, accumulator drain, epilogue
-constexpr int kIssuerWarp = 8;                        // warp 8: MMA issuer (one elected lane)
-constexpr int kWeightWarp = 9;                        // warp 9: weight-tile producer (bulk copies, one elected lane)
-constexpr int kTcThreads = 320;
+constexpr int kDrainWarps = 8;                        // warps 0-7: accumulator drain (TMEM -> registers) + epilogue
+constexpr int kLoaderWarp0 = 8;                       // warps 8-11: A loaders (cp.async)
+constexpr int kLoaderWarps = 4;
+constexpr int kLoaderThreads = kLoaderWarps * 32;
+constexpr int kIssuerWarp = 12;                       // warp 12: MMA issuer (one elected lane)
+constexpr int kWeightWarp = 13;                       // warp 13: weight-tile producer (bulk copies, one elected lane)
+constexpr int kTcThreads = 448;                       // 14 warps; registers are granted as for 16 (128 per thread)
 
 int g_tc_cluster = 1;         // CTAs per cluster = multicast width of the weight tiles (CPB_TC_CLUSTER, 1/2/4/8)
 int g_tc_clusters[3] = {0, 0, 0};   // co-resident clusters of the persistent grid, per BN instantiation (32/64/128)
@@ -104,7 +107,7 @@ tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p, const int mgroups, co
     __shared__ uint64_t full_bar[STAGES];     // A loader threads (cp.async completion) + weight bytes -> issuer
     __shared__ uint64_t empty_bar[STAGES];    // tensor cores of ALL CTAs of the cluster -> producers: stage is free everywhere
     __shared__ uint64_t chunk_bar[2];         // tensor core -> loaders: accumulator buffer b holds a finished chunk
-    __shared__ uint64_t drained_bar[2];       // loader warps -> issuer: buffer b was added to the register accumulators
+    __shared__ uint64_t drained_bar[2];       // drain warps -> issuer: buffer b was added to the register accumulators
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x;
@@ -121,9 +124,9 @@ tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p, const int mgroups, co
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], kLoaderWarps * 32 + 1); mbar_init(&empty_bar[s], (uint32_t)CS); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], kLoaderThreads + 1); mbar_init(&empty_bar[s], (uint32_t)CS); }
         mbar_init(&chunk_bar[0], 1); mbar_init(&chunk_bar[1], 1);
-        mbar_init(&drained_bar[0], kLoaderWarps); mbar_init(&drained_bar[1], kLoaderWarps);
+        mbar_init(&drained_bar[0], kDrainWarps); mbar_init(&drained_bar[1], kDrainWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc<Cfg::TMEM_COLS>(&tmem_slot);
@@ -143,11 +146,12 @@ tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p, const int mgroups, co
         // ================================ MMA issuer ================================
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+            const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
             int g = 0, gc = 0;                  // k-blocks / chunks issued so far (all tiles)
             long long prof[4] = {0, 0, 0, 0}, tlast = 0;
             if constexpr (PROF) tlast = clock64();
             const long long tstart = tlast;
-            for (int st = cl_id, nt = 0; st < total_st; st += cl_n, ++nt) {
+            for (int st = cl_id; st < total_st; st += cl_n) {
                 const int nkb = p.cls[st_z(st)].ntaps * kb_per_tap;
                 for (int kb = 0; kb < nkb; ++kb, ++g) {
                     const int s = g % STAGES;
@@ -164,16 +168,19 @@ tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p, const int mgroups, co
                     const uint64_t a_hi = make_desc(stage);
                     const uint64_t a_lo = make_desc(stage + A_TILE_BYTES);
                     const uint64_t b_hi = make_desc(stage + 2 * A_TILE_BYTES);
-                    const uint64_t b_lo = make_desc(stage + 2 * A_TILE_BYTES + B_TILE_BYTES);
-                    const uint32_t d_main = tmem_base + (uint32_t)(b * BN);
-                    const uint32_t d_cross = tmem_base + (uint32_t)(2 * BN + (nt & 1) * BN);
+                    // per 8-wide k-step:  [main | cross] (+)= a_hi x [b_hi | b_lo]   (ONE N = 2*BN MMA: the b_hi and b_lo
+                    //                                                  images are adjacent in the stage)
+                    //                      cross           += a_lo x b_hi
+                    // -- 20 KB of operand reads instead of 24 KB for three N = BN MMAs (the SS-mode MMA is bound by its
+                    // shared-memory operand reads), and 8 instead of 12 instructions per k-block
+                    const uint32_t d_main = tmem_base + (uint32_t)(b * 2 * BN);
+                    const uint32_t d_cross = d_main + (uint32_t)BN;
                     if (!(p.debug & 1))
 #pragma unroll
                     for (int ks = 0; ks < TBK / 8; ++ks) {
                         const uint64_t adv = (uint64_t)(ks * 2);      // 32 bytes per k-step, in 16-byte units
-                        umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, ((kb % CHUNK_KB) | ks) != 0 ? 1u : 0u);
-                        umma_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
-                        umma_tf32(d_cross, a_hi + adv, b_lo + adv, idesc, 1u);
+                        umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc2, ((kb % CHUNK_KB) | ks) != 0 ? 1u : 0u);
+                        umma_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, 1u);
                     }
                     umma_commit_mc(&empty_bar[s], cl_mask, CS > 1);
                     if (kb % CHUNK_KB == CHUNK_KB - 1 || kb == nkb - 1) { umma_commit(&chunk_bar[b]); ++gc; }
@@ -215,8 +222,8 @@ tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p, const int mgroups, co
             }
         }
         __syncwarp();
-    } else {
-        // ================================ A loaders / drain / epilogue ================================
+    } else if (warp >= kLoaderWarp0 && warp < kLoaderWarp0 + kLoaderWarps) {
+        // ================================ A loaders ================================
         // The tensor core ignores the 13 low mantissa bits of a TF32 operand (scripts/diag_trunc.py: bit-identical
         // results), so the raw fp32 activations ARE the "hi" operand; the "lo" operand (x - trunc(x)) comes from a
         // plane written by lo_plane_kernel before this launch.  A tile rows are therefore copied global -> swizzled
@@ -224,30 +231,32 @@ tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p, const int mgroups, co
         // counted on the stage's mbarrier (cp.async.mbarrier.arrive.noinc) -- no registers, no split, no stores,
         // no wait in the loader.  The loader warps are INSTRUCTION bound otherwise (8 warps feed a 768-cycle MMA
         // block per k-block), which is why the per-k-block code is kept this small.
-        const int a_chunk = tid & 7;
-        // row r = tid/8 + 32*i lives at (r/8)*1024 + (r%8)*128 + ((chunk ^ r%8) * 16): i only moves the 1 KB group
-        const uint32_t a_soff0 = (uint32_t)((tid >> 6) * 1024 + ((tid >> 3) & 7) * 128 + ((a_chunk ^ ((tid >> 3) & 7)) << 4));
+        const int tl = tid - kLoaderWarp0 * 32;      // 0..127
+        const int a_chunk = tl & 7;
+        // row r = tl/8 + 16*i lives at (r/8)*1024 + (r%8)*128 + ((chunk ^ r%8) * 16): i only moves the 1 KB group (2 per i)
+        const uint32_t a_soff0 = (uint32_t)((tl >> 6) * 1024 + ((tl >> 3) & 7) * 128 + ((a_chunk ^ ((tl >> 3) & 7)) << 4));
+        constexpr int RPT = TBM / (kLoaderThreads / 8);     // rows per thread: 8
 
-        // ---- A cursor: 8 threads cover the 128 bytes of one row, 32 rows per pass, 4 passes
+        // ---- A cursor: 8 threads cover the 128 bytes of one row, 16 rows per pass, 8 passes
         int stA = cl_id, tapA = 0, cA = 0;
         int ntapsA = 0;
         int offA = 0;                           // taps[tapA].src_off + cA: float offset added to the row bases
         uint32_t tapbitA = 1u;
         const TapClass* clsA = &p.cls[0];
-        uint32_t a_base[4];                     // float offset of the row's first tap position (< 2^31, checked at launch)
-        uint32_t a_taps[4];                     // bit t: tap t of this row is inside the source image (0: row beyond M)
+        uint32_t a_base[RPT];                     // float offset of the row's first tap position (< 2^31, checked at launch)
+        uint32_t a_taps[RPT];                     // bit t: tap t of this row is inside the source image (0: row beyond M)
         auto setup_rows = [&]() {
             clsA = &p.cls[st_z(stA)];
             ntapsA = clsA->ntaps;
             const int Wo = clsA->Wo, HoWo = clsA->Ho * Wo;
             const long long M = (long long)p.batch * HoWo;
             const uint32_t wo_magic = (uint32_t)((0x100000000ull + (uint32_t)Wo - 1) / (uint32_t)Wo);   // exact for rem < 65536
-            // first row by division, the other three are 32 positions apart
-            long long m = st_m0(stA) + (tid >> 3);
+            // first row by division, the others are 16 positions apart
+            long long m = st_m0(stA) + (tl >> 3);
             int n = (int)(m / HoWo);
             int rem = (int)(m - (long long)n * HoWo);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < RPT; ++i) {
                 const bool ok = m < M;
                 const int oy = (int)__umulhi((uint32_t)rem, wo_magic);
                 const int ox = rem - oy * Wo;
@@ -260,7 +269,7 @@ tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p, const int mgroups, co
                         if ((unsigned)(iy + clsA->taps[t].dy) < (unsigned)p.Hs && (unsigned)(ix + clsA->taps[t].dx) < (unsigned)p.Ws) bits |= 1u << t;
                 }
                 a_taps[i] = ok ? bits : 0u;
-                m += 32; rem += 32;
+                m += 16; rem += 16;
                 while (rem >= HoWo) { rem -= HoWo; ++n; }
             }
             offA = (int)clsA->taps[0].src_off;
@@ -271,12 +280,13 @@ tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p, const int mgroups, co
         auto issue_a = [&](uint32_t stage, uint64_t* full) {
             const uint32_t dst = stage + a_soff0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < RPT; ++i) {
                 const bool v = (a_taps[i] & tapbitA) != 0u;
                 const uint32_t off = v ? a_base[i] + (uint32_t)offA : 0u;
-                const uint32_t bytes = v ? 16u : 0u;                 // 0: the 16 destination bytes are zero-filled
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + i * 4096), "l"(p.src + off), "r"(bytes) : "memory");
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + A_TILE_BYTES + i * 4096), "l"(p.src_lo + off), "r"(bytes) : "memory");
+                const uint32_t bytes = (v && !(p.debug & 4)) ? 16u : 0u;   // 0: the 16 destination bytes are zero-filled
+                if (p.debug & 2) continue;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + i * 2048), "l"(p.src + off), "r"(bytes) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + A_TILE_BYTES + i * 2048), "l"(p.src_lo + off), "r"(bytes) : "memory");
             }
             asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(full)) : "memory");
             cA += TBK; offA += TBK;
@@ -293,6 +303,16 @@ tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p, const int mgroups, co
             }
         };
 
+        // ---- copy stream: the loaders run ahead of the tensor core by as many k-blocks as there are free stages
+        int sS = 0;                                 // stage of the next k-block and the parity its empty barrier
+        uint32_t phS = 1;                           // shows once free (fresh barrier: parity 1 counts as complete)
+        while (stA < total_st) {
+            mbar_wait(&empty_bar[sS], phS);
+            issue_a(smem_base + sS * STAGE_BYTES, &full_bar[sS]);
+            if (++sS == STAGES) { sS = 0; phS ^= 1u; }
+        }
+    } else if (warp < kDrainWarps) {
+        // ================================ accumulator drain + epilogue ================================
         // ---- register accumulators: this thread owns row (q*32 + lane) x columns [half*BN/2, +BN/2) of the tile
         //      being drained (stD)
         constexpr int HALF_COLS = BN / 2;
@@ -368,8 +388,7 @@ tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p, const int mgroups, co
 
         // ---- drain cursor: chunk `drained` belongs to super-tile stD, which has chunksD chunks left
         auto st_chunks = [&](int st) { return (p.cls[st_z(st)].ntaps * kb_per_tap + CHUNK_KB - 1) / CHUNK_KB; };
-        int drained = 0, ntD = 0;
-        long long epi_cycles = 0;
+        int drained = 0;
         // acc += 32 lanes x BN/2 columns of TMEM; two tcgen05.ld in flight per wait (a single one per round trip
         // costs ~200 cycles each while the MMAs are running)
         auto drain_cols = [&](uint32_t taddr) {
@@ -392,22 +411,25 @@ tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p, const int mgroups, co
         };
         int stD = cl_id;
         int chunksD = stD < total_st ? st_chunks(stD) : 0;
+        long long prof[4] = {0, 0, 0, 0}, tlast = 0;
+        if constexpr (PROF) tlast = clock64();
+        const long long tstart = tlast;
         auto drain_one = [&]() {
             const int b = drained & 1;
+            TC_PROF(3);
             mbar_wait(&chunk_bar[b], (uint32_t)((drained >> 1) & 1));
+            TC_PROF(0);
             tc_fence_after();
-            drain_cols(tmem_lane + (uint32_t)(b * BN));
-            if (chunksD == 1) drain_cols(tmem_lane + (uint32_t)(2 * BN + (ntD & 1) * BN));   // last chunk of the tile: + its cross-term tile
+            drain_cols(tmem_lane + (uint32_t)(b * 2 * BN));            // main term of the chunk
+            drain_cols(tmem_lane + (uint32_t)(b * 2 * BN + BN));       // its cross terms
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&drained_bar[b]);
             ++drained;
+            TC_PROF(1);
             if (--chunksD == 0) {
-                ++ntD;
-                long long e0 = 0;
-                if constexpr (PROF) e0 = clock64();
                 epilogue(stD);
-                if constexpr (PROF) epi_cycles += clock64() - e0;
+                TC_PROF(2);
 #pragma unroll
                 for (int i = 0; i < HALF_COLS; ++i) acc[i] = 0.f;
                 stD += cl_n;
@@ -415,40 +437,13 @@ tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p, const int mgroups, co
             }
         };
 
-        // ---- copy stream: the loaders run ahead of the tensor core by as many k-blocks as there are free stages
-        int gc = 0;                                 // chunks handed to the issuer so far
-        int sS = 0;                                 // stage of the next k-block and the parity its empty barrier
-        uint32_t phS = 1;                           // shows once free (fresh barrier: parity 1 counts as complete)
-        long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
-        if constexpr (PROF) tlast = clock64();
-        const long long tstart = tlast;
-        // single loop over the k-block stream; ONE inlined copy of the drain + epilogue code
-        int st = cl_id, kb = 0;
-        int nkb = st < total_st ? p.cls[st_z(st)].ntaps * kb_per_tap : 0;
-        for (;;) {
-            const bool more = st < total_st;
-            // late drain: chunk gc-2 retired long ago (the stage ring is no deeper than a chunk); at the end, everything
-            const int target = more ? ((kb & (CHUNK_KB - 1)) == 0 ? gc - 1 : 0) : gc;
-            while (drained < target) drain_one();
-            TC_PROF(2);
-            if (!more) break;
-            mbar_wait(&empty_bar[sS], phS);
-            TC_PROF(0);
-            issue_a(smem_base + sS * STAGE_BYTES, &full_bar[sS]);
-            TC_PROF(4);
-            if (++sS == STAGES) { sS = 0; phS ^= 1u; }
-            if ((kb & (CHUNK_KB - 1)) == CHUNK_KB - 1 || kb == nkb - 1) ++gc;
-            if (++kb == nkb) {
-                kb = 0;
-                st += cl_n;
-                if (st < total_st) nkb = p.cls[st_z(st)].ntaps * kb_per_tap;
-            }
-            TC_PROF(7);
-        }
+        // chunks are drained as soon as the tensor core finishes them; the issuer may run two chunks ahead (two
+        // accumulator buffers), which hides the epilogue of a tile behind the MMAs of the next one
+        while (stD < total_st) drain_one();
         if constexpr (PROF) {
             if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 5))
-                printf("tcprof   loader warp %d total %lld: wait_empty %lld drain+epi %lld (epi %lld) issue_a %lld loop %lld\n",
-                       warp, clock64() - tstart, prof[0], prof[2], epi_cycles, prof[4], prof[7]);
+                printf("tcprof   drain warp %d total %lld: wait_chunk %lld drain %lld epilogue %lld other %lld (chunks %d)\n",
+                       warp, clock64() - tstart, prof[0], prof[1], prof[2], prof[3], drained);
         }
     }
     tc_fence_before();

@@ -1,6 +1,6 @@
 for cs in 1 2; do
 echo "=== cluster $cs"
-CPB_TC_CLUSTER=$cs timeout 200 python scripts/diag_tc.py 2>&1 | grep -v "^  [a-z]" | tail -12
+CPB_TC_CLUSTER=$cs timeout 200 python scripts/diag_tc.py 2>&1 | grep "K=4096 pos\|K=576\|K=32 "
 CPB_TC_CLUSTER=$cs timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bc$cs.json 2>gpurun_out/bc$cs.err
 python - <<PY
 import json
