@@ -33,8 +33,10 @@ struct TcWgCfg {
     static constexpr int TMEM_COLS = BN == 128 ? 512 : (BN == 64 ? 256 : 128);
 };
 
-constexpr int kWgLoaderWarps = 8;
-constexpr int kWgThreads = kWgLoaderWarps * 32 + 32;      // + warp 8: MMA issuer (one elected lane)
+constexpr int kWgLoaderWarps = 8;                         // warps 0-7: A (big) loaders, accumulator drain, partial store
+constexpr int kWgBWarps = 4;                              // warps 8-11: B (small) loaders
+constexpr int kWgIssuerWarp = kWgLoaderWarps + kWgBWarps; // warp 12: MMA issuer (one elected lane)
+constexpr int kWgThreads = (kWgIssuerWarp + 1) * 32;
 
 template <int BN>
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -67,7 +69,7 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], kWgLoaderWarps); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], kWgLoaderWarps + kWgBWarps); mbar_init(&empty_bar[s], 1); }
         mbar_init(&chunk_bar[0], 1);
         mbar_init(&chunk_bar[1], 1);
         mbar_init(&drained_bar[0], kWgLoaderWarps);
@@ -81,8 +83,24 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
     const int nchunks = (nkb + CHUNK_KB - 1) / CHUNK_KB;
+    constexpr int BQ = BN / 4;                       // channel groups of the B tile
+    const int len = (int)(m_end - m_begin);          // reduction positions of this split
 
-    if (warp == kWgLoaderWarps) {
+    // 4x4 register transpose + split + store: x[j] = 4 channels at position j  ->  one chunk per channel
+    auto store_t = [&](uint32_t tile_hi, uint32_t tile_lo, const float4* x, const uint32_t* so) {
+        const float xs[4][4] = {{x[0].x, x[1].x, x[2].x, x[3].x}, {x[0].y, x[1].y, x[2].y, x[3].y},
+                                {x[0].z, x[1].z, x[2].z, x[3].z}, {x[0].w, x[1].w, x[2].w, x[3].w}};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float4 hi, lo;
+            split_tf32(xs[c][0], hi.x, lo.x); split_tf32(xs[c][1], hi.y, lo.y);
+            split_tf32(xs[c][2], hi.z, lo.z); split_tf32(xs[c][3], hi.w, lo.w);
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(tile_hi + so[c]), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(tile_lo + so[c]), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+        }
+    };
+
+    if (warp == kWgIssuerWarp) {
         // ================================ MMA issuer ================================
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
@@ -113,8 +131,63 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
             }
         }
         __syncwarp();
+    } else if (warp >= kWgLoaderWarps) {
+        // ================================ B (small) loaders ================================
+        // 128 threads = (channel group of 4 output channels) x (position block of 4 reduction positions), a
+        // quarter-warp again covering 128 contiguous bytes; BN = 128 needs two position blocks per thread, BN = 32
+        // leaves half of the threads idle.  Same 4x4 transpose + split + swizzled store as the A side.
+        constexpr int NCGH = BQ >= 8 ? BQ / 8 : 1;
+        constexpr int REPS = BN == 128 ? 2 : 1;
+        const int r = (tid - kWgLoaderWarps * 32) >> 3;           // 0..15
+        const int cgb = (r % NCGH) * 8 + (lane & 7);
+        const int mb0 = r / NCGH;                                  // BN 32: 0..15 (>= 8 idle), 64: 0..7, 128: 0..3 (+4)
+        const bool active = mb0 < 8;
+        uint32_t soffb[REPS][4];
+#pragma unroll
+        for (int rp = 0; rp < REPS; ++rp)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int mbb = mb0 + 4 * rp;
+                const int rb = BQ * c + cgb;
+                soffb[rp][c] = (uint32_t)((rb >> 3) * 1024 + (rb & 7) * 128 + ((mbb ^ (rb & 7)) << 4));
+            }
+        int relB = mb0 * 4;
+        const float* bptr = p.small + (m_begin + relB) * p.J + j0 + cgb * 4;
+        auto load_b = [&](float4 (*xb)[4]) {
+#pragma unroll
+            for (int rp = 0; rp < REPS; ++rp)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    xb[rp][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (active && relB + 16 * rp + j < len) xb[rp][j] = __ldg(reinterpret_cast<const float4*>(bptr + (16 * rp + j) * p.J));
+                }
+            relB += TBK;
+            bptr += TBK * p.J;
+        };
+        float4 xb0[REPS][4], xb1[REPS][4];
+        int sS = 0;
+        uint32_t phS = 1;
+        auto step_b = [&](int kb, float4 (*xb)[4]) {
+            const uint32_t stage = smem_base + sS * STAGE_BYTES + 2 * A_TILE_BYTES;
+            mbar_wait(&empty_bar[sS], phS);
+            if (active) {
+#pragma unroll
+                for (int rp = 0; rp < REPS; ++rp) store_t(stage, stage + B_TILE_BYTES, xb[rp], soffb[rp]);
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[sS]);
+            if (kb + 2 < nkb) load_b(xb);
+            if (++sS == STAGES) { sS = 0; phS ^= 1u; }
+        };
+        if (nkb > 0) load_b(xb0);
+        if (nkb > 1) load_b(xb1);
+        for (int kb = 0; kb < nkb; kb += 2) {
+            step_b(kb, xb0);
+            if (kb + 1 < nkb) step_b(kb + 1, xb1);
+        }
     } else {
-        // ================================ loaders / drain / partial store ================================
+        // ================================ A loaders / drain / partial store ================================
         // thread = (channel group cg of 4 channels, position block mb of 4 reduction positions).
         // A quarter-warp = 8 consecutive channel groups of ONE position: its LDG.128 is one contiguous 128-byte line
         // (the L1 data pipe charges a wavefront per 32-byte sector when a quarter-warp straddles lines).
@@ -130,20 +203,15 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
             const int tap = a_i / p.run;
             a_coloff = p.tap_off[tap] + (a_i - tap * p.run);
         }
-        constexpr int BQ = BN / 4;                       // channel groups of the B tile
-        const bool b_col_ok = cg < BQ;
-        uint32_t soff[4], soffb[4];
+        uint32_t soff[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const int ra = 32 * c + cg;
             soff[c] = (uint32_t)((ra >> 3) * 1024 + (ra & 7) * 128 + ((mb ^ (ra & 7)) << 4));
-            const int rb = BQ * c + (cg % BQ);
-            soffb[c] = (uint32_t)((rb >> 3) * 1024 + (rb & 7) * 128 + ((mb ^ (rb & 7)) << 4));
         }
 
         // position cursor of this thread's NEXT load (k-block kbL): image n, position rem = oy*Wo + ox inside it.
         // Advancing by a k-block (32 positions) needs no division: oy comes from a multiply-high by ceil(2^32 / Wo).
-        const int len = (int)(m_end - m_begin);                    // reduction positions of this split
         const uint32_t wo_magic = (uint32_t)((0x100000000ull + (uint32_t)p.Wo - 1) / (uint32_t)p.Wo);
         const int dx = p.sstride * p.big_pitch;                              // next position in the row
         const int drow = (p.sstride * p.Wb - p.Wo * p.sstride) * p.big_pitch;   // ... wrapping to the next row
@@ -154,8 +222,7 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
             nL = (int)(m / HoWo);
             remL = (int)(m - (long long)nL * HoWo);
         }
-        const float* bptr = p.small + (m_begin + relL) * p.J + j0 + cg * 4;
-        auto load_regs = [&](float4* areg, float4* breg) {
+        auto load_regs = [&](float4* areg) {
             int oy = (int)__umulhi((uint32_t)remL, wo_magic);
             int ox = remL - oy * p.Wo;
             uint32_t off = (uint32_t)nL * (uint32_t)p.big_img + (uint32_t)((oy * p.sstride * p.Wb + ox * p.sstride) * p.big_pitch) + (uint32_t)a_coloff;
@@ -163,30 +230,13 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
             for (int j = 0; j < 4; ++j) {
                 const bool v = relL + j < len;
                 areg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                breg[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (v && a_col_ok) areg[j] = __ldg(reinterpret_cast<const float4*>(p.big + off));
-                if (v && b_col_ok) breg[j] = __ldg(reinterpret_cast<const float4*>(bptr + j * p.J));
                 off += (uint32_t)dx;
                 if (++ox == p.Wo) { ox = 0; off += (uint32_t)drow; if (++oy == p.Ho) { oy = 0; off += (uint32_t)dimg; } }
             }
             relL += TBK;
-            bptr += TBK * p.J;
             remL += TBK;
             while (remL >= HoWo) { remL -= HoWo; ++nL; }
-        };
-
-        // 4x4 register transpose + split + store: x[j] = 4 channels at position j  ->  one chunk per channel
-        auto store_t = [&](uint32_t tile_hi, uint32_t tile_lo, const float4* x, const uint32_t* so) {
-            const float xs[4][4] = {{x[0].x, x[1].x, x[2].x, x[3].x}, {x[0].y, x[1].y, x[2].y, x[3].y},
-                                    {x[0].z, x[1].z, x[2].z, x[3].z}, {x[0].w, x[1].w, x[2].w, x[3].w}};
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float4 hi, lo;
-                split_tf32(xs[c][0], hi.x, lo.x); split_tf32(xs[c][1], hi.y, lo.y);
-                split_tf32(xs[c][2], hi.z, lo.z); split_tf32(xs[c][3], hi.w, lo.w);
-                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(tile_hi + so[c]), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
-                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(tile_lo + so[c]), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
-            }
         };
 
         constexpr int HALF_COLS = BN / 2;
@@ -229,28 +279,27 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
 
         // two k-blocks of operand rows are in flight per thread (register double buffer): with one, every
         // k-block costs a full L2 round trip per warp
-        float4 xa0[4], xb0[4], xa1[4], xb1[4];
+        float4 xa0[4], xa1[4];
         int sS = 0;                                 // stage of the k-block being stored and the parity its empty
         uint32_t phS = 1;                           // barrier shows once free (fresh barrier: parity 1 counts as complete)
-        auto step = [&](int kb, float4* xa, float4* xb) {
+        auto step = [&](int kb, float4* xa) {
             const uint32_t stage = smem_base + sS * STAGE_BYTES;
             mbar_wait(&empty_bar[sS], phS);
             if ((kb & (CHUNK_KB - 1)) == 0) {
                 while (drained < kb / CHUNK_KB - 1) drain_one();
             }
             store_t(stage, stage + A_TILE_BYTES, xa, soff);
-            if (b_col_ok) store_t(stage + 2 * A_TILE_BYTES, stage + 2 * A_TILE_BYTES + B_TILE_BYTES, xb, soffb);
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&full_bar[sS]);
-            if (kb + 2 < nkb) load_regs(xa, xb);
+            if (kb + 2 < nkb) load_regs(xa);
             if (++sS == STAGES) { sS = 0; phS ^= 1u; }
         };
-        if (nkb > 0) load_regs(xa0, xb0);
-        if (nkb > 1) load_regs(xa1, xb1);
+        if (nkb > 0) load_regs(xa0);
+        if (nkb > 1) load_regs(xa1);
         for (int kb = 0; kb < nkb; kb += 2) {
-            step(kb, xa0, xb0);
-            if (kb + 1 < nkb) step(kb + 1, xa1, xb1);
+            step(kb, xa0);
+            if (kb + 1 < nkb) step(kb + 1, xa1);
         }
 
         if (nkb > 0) {
