@@ -5,8 +5,8 @@
 //   edge_gather_kernel : small[b,i,j,0:32] = epi( sum_{kh,kw,c<CB} big4[b,2i+kh,2j+kw,c] * W[kh,kw,c,0:32] )
 //                        big4 is the float4-per-pixel padded image (prep_frames / recon_loss write it).
 //                        conv1 forward (epi = bias+ReLU) and conv2d_transpose(deconv4) data-gradient (epi = ReLU mask).
-//                        One thread = 2 horizontally adjacent output pixels x 32 channels: every weight float4 read
-//                        from shared memory (warp-broadcast) feeds 8 FMAs, the padded channel is skipped.
+//                        One thread = 4 horizontally adjacent output pixels x 16 channels: every weight float4 read
+//                        from shared memory (warp-broadcast) feeds 16 FMAs, the padded channel is skipped.
 //   edge_wgrad_kernel  : gw[kh,kw,c,j] = sum_{b,i,j'} big4[b,2i+kh,2j'+kw,c] * small[b,i,j',j]   (Conv2DBackpropFilter)
 //                        One CTA walks output rows; per row it stages the 4 big rows and the small row in shared
 //                        memory (cp.async), each warp accumulates the FULL [16*CB x 32] tile over its share of the
@@ -20,61 +20,76 @@ namespace {
 
 constexpr int EH = 80, EW = 160, SH = 39, SW = 79, SC = 32;   // big image (pixels), small image, small channels
 
+// One thread = 4 horizontally adjacent output pixels x 16 of the 32 channels (lane parity picks the half).  The
+// weights are read from shared memory as warp-broadcast LDS.128; such a load still writes 512 bytes of registers,
+// i.e. occupies the 128 B/clk shared-memory return path for 4 cycles, so what matters is FMAs per LDS.128:
+// 4 pixels x 4 channels = 16 (two pixels x 32 channels per thread gave 8 and left the kernel LDS-bound at twice
+// its FMA time).
 template <int CB, int EPI>   // EPI 0: bias + ReLU, 1: multiply by (mask > 0)
 __global__ void __launch_bounds__(128)
 edge_gather_kernel(const float4* __restrict__ big4, const float* __restrict__ w, const float* __restrict__ bias,
-                   const float* __restrict__ mask, float* __restrict__ small, long long npairs) {
+                   const float* __restrict__ mask, float* __restrict__ small, long long nwork) {
     __shared__ __align__(16) float ws[16 * CB * SC];
     for (int i = threadIdx.x; i < 16 * CB * SC; i += blockDim.x) ws[i] = w[i];
     __syncthreads();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= npairs) return;
-    constexpr int PW = (SW + 1) / 2;                     // 40 pairs per output row
-    const int px = (int)(t % PW);
-    const int oy = (int)((t / PW) % SH);
-    const long long n = t / (PW * SH);
-    const int ox = px * 2;
-    const bool second = ox + 1 < SW;
+    if (t >= nwork) return;
+    constexpr int NPX = 4;                               // output pixels per thread
+    constexpr int HC = SC / 2;                           // channels per thread
+    constexpr int GW = (SW + NPX - 1) / NPX;             // 20 pixel groups per output row
+    const int ch0 = (int)(t & 1) * HC;
+    const long long grp = t >> 1;
+    const int gx = (int)(grp % GW);
+    const int oy = (int)((grp / GW) % SH);
+    const long long n = grp / (GW * SH);
+    const int ox = gx * NPX;
+    const int nvalid = SW - ox < NPX ? SW - ox : NPX;    // 4, or 3 in the last group of a row
 
-    float acc0[SC], acc1[SC];
+    float acc[NPX][HC];
 #pragma unroll
-    for (int j = 0; j < SC; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+    for (int q = 0; q < NPX; ++q)
+#pragma unroll
+        for (int j = 0; j < HC; ++j) acc[q][j] = 0.f;
 
     const float4* row0 = big4 + (n * EH + 2 * oy) * EW + 2 * ox;
+    constexpr int NIN = 2 * (NPX - 1) + 4;               // 10 input pixels per kernel row
 #pragma unroll
     for (int kh = 0; kh < 4; ++kh) {
-        float4 in[6];
+        float4 in[NIN];
 #pragma unroll
-        for (int q = 0; q < 6; ++q) in[q] = (q < 4 || second) ? __ldg(row0 + kh * EW + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < NIN; ++q) in[q] = (2 * ox + q < EW) ? __ldg(row0 + kh * EW + q) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int kw = 0; kw < 4; ++kw) {
 #pragma unroll
             for (int c = 0; c < CB; ++c) {
-                const float a0 = c == 0 ? in[kw].x : (c == 1 ? in[kw].y : in[kw].z);
-                const float a1 = c == 0 ? in[kw + 2].x : (c == 1 ? in[kw + 2].y : in[kw + 2].z);
-                const float* wr = &ws[((kh * 4 + kw) * CB + c) * SC];
+                float a[NPX];
 #pragma unroll
-                for (int j4 = 0; j4 < SC / 4; ++j4) {
+                for (int q = 0; q < NPX; ++q) a[q] = c == 0 ? in[kw + 2 * q].x : (c == 1 ? in[kw + 2 * q].y : in[kw + 2 * q].z);
+                const float* wr = &ws[((kh * 4 + kw) * CB + c) * SC + ch0];
+#pragma unroll
+                for (int j4 = 0; j4 < HC / 4; ++j4) {
                     const float4 wv = *reinterpret_cast<const float4*>(wr + j4 * 4);
-                    acc0[j4 * 4 + 0] = fmaf(a0, wv.x, acc0[j4 * 4 + 0]); acc1[j4 * 4 + 0] = fmaf(a1, wv.x, acc1[j4 * 4 + 0]);
-                    acc0[j4 * 4 + 1] = fmaf(a0, wv.y, acc0[j4 * 4 + 1]); acc1[j4 * 4 + 1] = fmaf(a1, wv.y, acc1[j4 * 4 + 1]);
-                    acc0[j4 * 4 + 2] = fmaf(a0, wv.z, acc0[j4 * 4 + 2]); acc1[j4 * 4 + 2] = fmaf(a1, wv.z, acc1[j4 * 4 + 2]);
-                    acc0[j4 * 4 + 3] = fmaf(a0, wv.w, acc0[j4 * 4 + 3]); acc1[j4 * 4 + 3] = fmaf(a1, wv.w, acc1[j4 * 4 + 3]);
+#pragma unroll
+                    for (int q = 0; q < NPX; ++q) {
+                        acc[q][j4 * 4 + 0] = fmaf(a[q], wv.x, acc[q][j4 * 4 + 0]);
+                        acc[q][j4 * 4 + 1] = fmaf(a[q], wv.y, acc[q][j4 * 4 + 1]);
+                        acc[q][j4 * 4 + 2] = fmaf(a[q], wv.z, acc[q][j4 * 4 + 2]);
+                        acc[q][j4 * 4 + 3] = fmaf(a[q], wv.w, acc[q][j4 * 4 + 3]);
+                    }
                 }
             }
         }
     }
-    const long long off = ((n * SH + oy) * SW + ox) * SC;
+    const long long off = ((n * SH + oy) * SW + ox) * SC + ch0;
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        if (half == 1 && !second) break;
-        float* acc = half == 0 ? acc0 : acc1;
-        const long long o = off + half * SC;
+    for (int q = 0; q < NPX; ++q) {
+        if (q >= nvalid) break;
+        const long long o = off + q * SC;
 #pragma unroll
-        for (int j4 = 0; j4 < SC / 4; ++j4) {
-            float4 v = make_float4(acc[j4 * 4], acc[j4 * 4 + 1], acc[j4 * 4 + 2], acc[j4 * 4 + 3]);
+        for (int j4 = 0; j4 < HC / 4; ++j4) {
+            float4 v = make_float4(acc[q][j4 * 4], acc[q][j4 * 4 + 1], acc[q][j4 * 4 + 2], acc[q][j4 * 4 + 3]);
             if (EPI == 0) {
-                const float4 b = *reinterpret_cast<const float4*>(bias + j4 * 4);
+                const float4 b = *reinterpret_cast<const float4*>(bias + ch0 + j4 * 4);
                 v.x = fmaxf(v.x + b.x, 0.f); v.y = fmaxf(v.y + b.y, 0.f); v.z = fmaxf(v.z + b.z, 0.f); v.w = fmaxf(v.w + b.w, 0.f);
             } else {
                 const float4 mk = __ldg(reinterpret_cast<const float4*>(mask + o + j4 * 4));
@@ -177,7 +192,7 @@ edge_wgrad_kernel(const float* __restrict__ big4, const float* __restrict__ smal
 int32_t launch_edge_gather(const float* big4, int cb, const float* w, const float* bias, const float* mask,
                            float* small, int batch, cudaStream_t stream) {
     CPB_REQUIRE(cb == 1 || cb == 3, "edge_gather: channels must be 1 or 3");
-    const long long npairs = (long long)batch * SH * ((SW + 1) / 2);
+    const long long npairs = 2LL * batch * SH * ((SW + 3) / 4);      // (4-pixel group, channel half) work items
     if (npairs == 0) return CPB_OK;
     const unsigned blocks = (unsigned)cdiv(npairs, 128);
     const float4* b4 = reinterpret_cast<const float4*>(big4);

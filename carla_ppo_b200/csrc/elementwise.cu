@@ -29,27 +29,28 @@ __global__ void prep_frames_kernel(const T* __restrict__ src, float scale, long 
 }
 
 // ------------------------------------------------------------------------------------------
-// output layer: conv2d_transpose 4x4 s2, 32 -> CT channels.  One thread = TWO horizontally adjacent 2x2 output
-// quads (qx0, qx0+1): they share the middle input pixel and, more importantly, every weight float4 read from
-// shared memory (warp-broadcast) now feeds 8 FMAs instead of 4.
+// output layer: conv2d_transpose 4x4 s2, 32 -> CT channels.
 // ------------------------------------------------------------------------------------------
-template <int CT>
+// One thread = NQ horizontally adjacent 2x2 output quads.  Every weight float4 read from shared memory
+// (warp-broadcast LDS.128, which occupies the 128 B/clk return path for 4 cycles) feeds NQ x 4 FMAs; with 2 quads
+// per thread the kernel was LDS-bound at 4x its FMA time.
+template <int CT, int NQ>
 __global__ void __launch_bounds__(128)
 deconv4_fwd_kernel(const float* __restrict__ small, const float* __restrict__ w, const float* __restrict__ bias,
-                   long long npairs, float* __restrict__ logits_p, float* __restrict__ sigm) {
-    constexpr int HS = 39, WS = 79, CS = 32, QH = 40, QW = 80, HB = 80, WB = 160, PW = QW / 2;
+                   long long nwork, float* __restrict__ logits_p, float* __restrict__ sigm) {
+    constexpr int HS = 39, WS = 79, CS = 32, QH = 40, QW = 80, HB = 80, WB = 160, PW = QW / NQ;
     __shared__ __align__(16) float ws[16 * CT * CS];
     for (int i = threadIdx.x; i < 16 * CT * CS; i += blockDim.x) ws[i] = w[i];
     __syncthreads();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= npairs) return;
-    const int qx0 = (int)(t % PW) * 2;
+    if (t >= nwork) return;
+    const int qx0 = (int)(t % PW) * NQ;
     const int qy = (int)((t / PW) % QH);
     const long long n = t / (PW * QH);
 
-    float acc[2][2][2][CT];     // [quad][py][px][c]
+    float acc[NQ][2][2][CT];     // [quad][py][px][c]
 #pragma unroll
-    for (int q = 0; q < 2; ++q)
+    for (int q = 0; q < NQ; ++q)
 #pragma unroll
         for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -62,15 +63,15 @@ deconv4_fwd_kernel(const float* __restrict__ small, const float* __restrict__ w,
         const int iy = qy - j;
         if (iy < 0 || iy >= HS) continue;
         const float* rowp = small + ((n * HS + iy) * WS) * CS;
-        // input pixels p = qx0-1, qx0, qx0+1 ; quad q uses pixel (q + 1 - i) for tap column i
-        bool pv[3];
+        // input pixels p = qx0-1 .. qx0+NQ-1 ; quad q uses pixel (q + 1 - i) for tap column i
+        bool pv[NQ + 1];
 #pragma unroll
-        for (int p = 0; p < 3; ++p) pv[p] = (unsigned)(qx0 - 1 + p) < (unsigned)WS;
+        for (int p = 0; p < NQ + 1; ++p) pv[p] = (unsigned)(qx0 - 1 + p) < (unsigned)WS;
 #pragma unroll
         for (int c4 = 0; c4 < CS / 4; ++c4) {
-            float4 x[3];
+            float4 x[NQ + 1];
 #pragma unroll
-            for (int p = 0; p < 3; ++p)
+            for (int p = 0; p < NQ + 1; ++p)
                 x[p] = pv[p] ? __ldg(reinterpret_cast<const float4*>(rowp + (qx0 - 1 + p) * CS) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int i = 0; i < 2; ++i)
@@ -83,7 +84,7 @@ deconv4_fwd_kernel(const float* __restrict__ small, const float* __restrict__ w,
                         for (int c = 0; c < CT; ++c) {
                             const float4 wv = *reinterpret_cast<const float4*>(&ws[(tap * CT + c) * CS + c4 * 4]);
 #pragma unroll
-                            for (int q = 0; q < 2; ++q) {
+                            for (int q = 0; q < NQ; ++q) {
                                 const float4 xv = x[q + 1 - i];
                                 float s = acc[q][py][px][c];
                                 s = fmaf(xv.x, wv.x, s); s = fmaf(xv.y, wv.y, s);
@@ -95,7 +96,7 @@ deconv4_fwd_kernel(const float* __restrict__ small, const float* __restrict__ w,
         }
     }
 #pragma unroll
-    for (int q = 0; q < 2; ++q)
+    for (int q = 0; q < NQ; ++q)
 #pragma unroll
         for (int py = 0; py < 2; ++py)
 #pragma unroll
@@ -236,31 +237,51 @@ __global__ void finalize_losses_kernel(const float* __restrict__ frame_loss, con
 // column sums (bias gradients): pass 1 -> partial[blocks][pitch]
 // ------------------------------------------------------------------------------------------
 constexpr int kColsumMaxBlocks = 148 * 8;
-static long long colsum_rows_per_block(long long rows) {
-    long long rpb = (rows + kColsumMaxBlocks - 1) / kColsumMaxBlocks;
-    if (rpb < 256) rpb = 256;
-    return (rpb + 255) / 256 * 256;
+// number of row-chunk blocks; block b sums the row tiles b, b + nblocks, b + 2 nblocks, ... (a tile = the rows one
+// pass of the block covers), so that at any moment the resident blocks read one contiguous stretch of memory.
+// (Giving each block ONE contiguous range made the ~1200 concurrent streams start 1.3 MB apart and ran the
+// [12.6M x 32] sums at a quarter of the HBM rate.)
+static long long colsum_blocks(long long rows, int pitch) {
+    const int c4_total = pitch >> 2;
+    const int cw = c4_total < 256 ? c4_total : 256;
+    const long long tiles = (rows + (256 / cw) - 1) / (256 / cw);
+    long long nb = (tiles + 7) / 8;                        // at least 8 tiles per block
+    if (nb > kColsumMaxBlocks) nb = kColsumMaxBlocks;
+    return nb < 1 ? 1 : nb;
 }
 
 __global__ void __launch_bounds__(256)
-colsum_kernel(const float* __restrict__ g, long long rows, long long rows_per_block, int pitch,
-              float* __restrict__ partial) {
-    // blockIdx.x: row chunk; blockIdx.y: chunk of 256 float4 columns
+colsum_kernel(const float* __restrict__ g, long long rows, int pitch, float* __restrict__ partial) {
+    // blockIdx.x: row-tile residue; blockIdx.y: chunk of 256 float4 columns
     const int c4_total = pitch >> 2;
     const int cw = c4_total < 256 ? c4_total : 256;        // float4 columns handled by this block
-    const int lanes_r = 256 / cw;                           // row lanes
+    const int lanes_r = 256 / cw;                           // rows per tile
     const int cc = threadIdx.x % cw;
     const int rr = threadIdx.x / cw;
     const int col4 = blockIdx.y * 256 + cc;
-    const long long r0 = (long long)blockIdx.x * rows_per_block;
-    long long r1 = r0 + rows_per_block;
-    if (r1 > rows) r1 = rows;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (col4 < c4_total && rr < lanes_r) {
-        for (long long r = r0 + rr; r < r1; r += lanes_r) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(g + r * pitch) + col4);
+        // 8 independent loads in flight per thread; the summation order is fixed (deterministic)
+        const float4* base = reinterpret_cast<const float4*>(g) + col4;
+        const long long p4 = pitch >> 2;
+        const long long step = (long long)gridDim.x * lanes_r;
+        long long r = (long long)blockIdx.x * lanes_r + rr;
+        float4 a2 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (; r + 7 * step < rows; r += 8 * step) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldg(base + (r + u * step) * p4);
+#pragma unroll
+            for (int u = 0; u < 8; u += 2) {
+                acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+                a2.x += v[u + 1].x; a2.y += v[u + 1].y; a2.z += v[u + 1].z; a2.w += v[u + 1].w;
+            }
+        }
+        for (; r < rows; r += step) {
+            const float4 v = __ldg(base + r * p4);
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
+        acc.x += a2.x; acc.y += a2.y; acc.z += a2.z; acc.w += a2.w;
     }
     __shared__ float4 red[256];
     red[threadIdx.x] = acc;
@@ -367,11 +388,14 @@ int32_t launch_prep_frames(const void* src, int dtype, float scale, int cin, lon
 
 int32_t launch_deconv4_fwd(const float* small, const float* w, const float* bias, int batch, int ct,
                            float* logits_p, float* sigm, cudaStream_t stream) {
-    const long long npairs = (long long)batch * 40 * 40;     // pairs of 2x2 output quads
+    static const int nq = [] { const char* e = getenv("CPB_DECONV4_NQ"); return e && atoi(e) == 8 ? 8 : 4; }();
+    const long long npairs = (long long)batch * 40 * (80 / nq);     // groups of nq horizontally adjacent 2x2 output quads
     if (npairs == 0) return CPB_OK;
     const unsigned blocks = (unsigned)cdiv(npairs, 128);
-    if (ct == 3) deconv4_fwd_kernel<3><<<blocks, 128, 0, stream>>>(small, w, bias, npairs, logits_p, sigm);
-    else if (ct == 1) deconv4_fwd_kernel<1><<<blocks, 128, 0, stream>>>(small, w, bias, npairs, logits_p, sigm);
+    if (ct == 3 && nq == 8) deconv4_fwd_kernel<3, 8><<<blocks, 128, 0, stream>>>(small, w, bias, npairs, logits_p, sigm);
+    else if (ct == 3) deconv4_fwd_kernel<3, 4><<<blocks, 128, 0, stream>>>(small, w, bias, npairs, logits_p, sigm);
+    else if (ct == 1 && nq == 8) deconv4_fwd_kernel<1, 8><<<blocks, 128, 0, stream>>>(small, w, bias, npairs, logits_p, sigm);
+    else if (ct == 1) deconv4_fwd_kernel<1, 4><<<blocks, 128, 0, stream>>>(small, w, bias, npairs, logits_p, sigm);
     else CPB_REQUIRE(false, "deconv4: target_channels must be 1 or 3");
     CPB_LAUNCHED();
     return CPB_OK;
@@ -430,7 +454,7 @@ int32_t launch_finalize_losses(const float* frame_loss, const float* kl_rows, in
 }
 
 long long colsum_scratch_floats(long long rows, int pitch) {
-    return (long long)cdiv(rows, colsum_rows_per_block(rows)) * pitch;
+    return colsum_blocks(rows, pitch) * pitch;
 }
 
 int32_t launch_colsum(const float* g, long long rows, int pitch, int c_real, float* out, float* scratch,
@@ -438,10 +462,9 @@ int32_t launch_colsum(const float* g, long long rows, int pitch, int c_real, flo
     CPB_REQUIRE(pitch % 4 == 0, "colsum: pitch must be a multiple of 4");
     if (rows == 0) return CPB_OK;
     ProfScope prof("bias_grad.colsum", stream);
-    const long long rpb = colsum_rows_per_block(rows);
-    const int nblocks = cdiv(rows, rpb);
-    dim3 grid((unsigned)nblocks, (unsigned)cdiv(pitch / 4, 256));
-    colsum_kernel<<<grid, 256, 0, stream>>>(g, rows, rpb, pitch, scratch);
+    const int nblocks = (int)colsum_blocks(rows, pitch);
+    dim3 grid((unsigned)nblocks, (unsigned)cdiv(pitch >> 2, 256));
+    colsum_kernel<<<grid, 256, 0, stream>>>(g, rows, pitch, scratch);
     CPB_LAUNCHED();
     colsum_final_kernel<<<cdiv(c_real, 8), 256, 0, stream>>>(scratch, nblocks, pitch, c_real, out);
     CPB_LAUNCHED();
