@@ -57,7 +57,8 @@ struct TapGemmParams {
     // tensor-core path only: K-major per-tap [N][C] weight blocks, pre-split into hi / lo (tc_tapgemm.cu)
     const float* wk_hi;
     const float* wk_lo;
-    const float* src_lo;  // tensor-core path only: lo plane of src (launch_lo_plane), same indexing as src
+    const float* src_lo;  // tensor-core path only: lo plane of src (x - trunc_tf32(x)), same indexing as src
+    float* dst_lo;        // tensor-core path only: if set, the epilogue also writes the lo plane of dst (for the next layer)
     // tensor-core path only: quad-fused scatter form.  One GEMM row = one 2x2 output quad (qy, qx); the N axis is
     // (parity class, cb) = 4*quad_cb columns; cls[0] holds the union window taps (2x2 for k=4, 3x3 for k=5) and the
     // weight blocks carry zeros where a class does not use a tap.  The A tile is loaded once for all four classes.

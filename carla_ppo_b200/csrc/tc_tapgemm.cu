@@ -382,6 +382,11 @@ tc_tapgemm_kernel(const __grid_constant__ TapGemmParams p, const int mgroups, co
                         o.z = mks[u].z > 0.f ? o.z : 0.f; o.w = mks[u].w > 0.f ? o.w : 0.f;
                     }
                     *reinterpret_cast<float4*>(p.dst + offs[u]) = o;
+                    if (p.dst_lo != nullptr) {           // second TF32 operand of the consumer layer
+                        float4 h, l;
+                        split_tf32(o.x, h.x, l.x); split_tf32(o.y, h.y, l.y); split_tf32(o.z, h.z, l.z); split_tf32(o.w, h.w, l.w);
+                        *reinterpret_cast<float4*>(p.dst_lo + offs[u]) = l;
+                    }
                 }
             }
         };

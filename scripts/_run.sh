@@ -4,7 +4,7 @@ import json
 try:
     d=json.loads(open("gpurun_out/bc1.json").read().strip().splitlines()[-1])
     print(round(d["value"]), d["ms_per_step"], "e2e", round(d["e2e"]["value"]))
-    g=d["roofline"]["groups_ms_per_step"]; print({k:round(v,2) for k,v in g.items() if v>0.3})
+    g=d["roofline"]["groups_ms_per_step"]; print({k:round(v,2) for k,v in g.items() if v>0.5})
 except Exception as e:
     print("failed", e); print(open("gpurun_out/bc1.err").read()[-1500:])
 PY
