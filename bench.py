@@ -42,8 +42,9 @@ MAC = {"conv1": 4_732_416, "conv2": 22_413_312, "conv3": 18_874_368, "conv4": 12
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the labelled kernel group, from the committed ncu --set full
-# capture profiles/r1_ncu_full_raw_tc.csv (B=4096, second train step)
-NCU_DRAM_BYTES_PER_LAUNCH = {"deconv3.wgrad": 2.3399e9, "conv2.fwd": 3.0326e9, "conv3.fwd": 1.3042e9}
+# capture profiles/r1_ncu_full_raw_final_tc.csv (B=4096, second train step; table in profiles/r1_ncu_summary_final.md)
+NCU_DRAM_BYTES_PER_LAUNCH = {"deconv3.wgrad": 2.395e9, "deconv3.dgrad": 5.364e9, "deconv3.fwd": 3.005e9,
+                             "conv2.fwd": 4.535e9, "conv2.dgrad": 4.636e9, "conv2.wgrad": 2.359e9}
 
 
 def load_peaks():

@@ -35,9 +35,9 @@ edge_gather_kernel(const float4* __restrict__ big4, const float* __restrict__ w,
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nwork) return;
     constexpr int NPX = 4;                               // output pixels per thread
-    constexpr int HC = SC / 2;                           // channels per thread
-    constexpr int GW = (SW + NPX - 1) / NPX;             // 20 pixel groups per output row
-    const int ch0 = (int)(t & 1) * HC;
+    constexpr int HC = SC / 2;                           // channels per thread: the float4 groups 2*j4 + par, so that
+    constexpr int GW = (SW + NPX - 1) / NPX;             // a lane pair's stores fill whole 32-byte sectors
+    const int par = (int)(t & 1);
     const long long grp = t >> 1;
     const int gx = (int)(grp % GW);
     const int oy = (int)((grp / GW) % SH);
@@ -65,10 +65,10 @@ edge_gather_kernel(const float4* __restrict__ big4, const float* __restrict__ w,
                 float a[NPX];
 #pragma unroll
                 for (int q = 0; q < NPX; ++q) a[q] = c == 0 ? in[kw + 2 * q].x : (c == 1 ? in[kw + 2 * q].y : in[kw + 2 * q].z);
-                const float* wr = &ws[((kh * 4 + kw) * CB + c) * SC + ch0];
+                const float* wr = &ws[((kh * 4 + kw) * CB + c) * SC + par * 4];
 #pragma unroll
                 for (int j4 = 0; j4 < HC / 4; ++j4) {
-                    const float4 wv = *reinterpret_cast<const float4*>(wr + j4 * 4);
+                    const float4 wv = *reinterpret_cast<const float4*>(wr + j4 * 8);
 #pragma unroll
                     for (int q = 0; q < NPX; ++q) {
                         acc[q][j4 * 4 + 0] = fmaf(a[q], wv.x, acc[q][j4 * 4 + 0]);
@@ -80,7 +80,7 @@ edge_gather_kernel(const float4* __restrict__ big4, const float* __restrict__ w,
             }
         }
     }
-    const long long off = ((n * SH + oy) * SW + ox) * SC + ch0;
+    const long long off = ((n * SH + oy) * SW + ox) * SC + par * 4;
 #pragma unroll
     for (int q = 0; q < NPX; ++q) {
         if (q >= nvalid) break;
@@ -89,18 +89,18 @@ edge_gather_kernel(const float4* __restrict__ big4, const float* __restrict__ w,
         for (int j4 = 0; j4 < HC / 4; ++j4) {
             float4 v = make_float4(acc[q][j4 * 4], acc[q][j4 * 4 + 1], acc[q][j4 * 4 + 2], acc[q][j4 * 4 + 3]);
             if (EPI == 0) {
-                const float4 b = *reinterpret_cast<const float4*>(bias + ch0 + j4 * 4);
+                const float4 b = *reinterpret_cast<const float4*>(bias + par * 4 + j4 * 8);
                 v.x = fmaxf(v.x + b.x, 0.f); v.y = fmaxf(v.y + b.y, 0.f); v.z = fmaxf(v.z + b.z, 0.f); v.w = fmaxf(v.w + b.w, 0.f);
             } else {
-                const float4 mk = __ldg(reinterpret_cast<const float4*>(mask + o + j4 * 4));
+                const float4 mk = __ldg(reinterpret_cast<const float4*>(mask + o + j4 * 8));
                 v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f; v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
             }
-            *reinterpret_cast<float4*>(small + o + j4 * 4) = v;
+            *reinterpret_cast<float4*>(small + o + j4 * 8) = v;
             if (small_lo != nullptr) {               // second TF32 operand of the tensor-core layer that consumes `small`
                 float4 l;
                 l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
                 l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-                *reinterpret_cast<float4*>(small_lo + o + j4 * 4) = l;
+                *reinterpret_cast<float4*>(small_lo + o + j4 * 8) = l;
             }
         }
     }
