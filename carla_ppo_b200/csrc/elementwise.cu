@@ -32,8 +32,7 @@ __global__ void prep_frames_kernel(const T* __restrict__ src, float scale, long 
 // output layer: conv2d_transpose 4x4 s2, 32 -> CT channels.
 // ------------------------------------------------------------------------------------------
 // One thread = NQ horizontally adjacent 2x2 output quads.  Every weight float4 read from shared memory
-// (warp-broadcast LDS.128, which occupies the 128 B/clk return path for 4 cycles) feeds NQ x 4 FMAs; with 2 quads
-// per thread the kernel was LDS-bound at 4x its FMA time.
+// (warp-broadcast LDS.128, which occupies the 128 B/clk return path for 4 cycles) feeds NQ x 4 FMAs.
 template <int CT, int NQ>
 __global__ void __launch_bounds__(128)
 deconv4_fwd_kernel(const float* __restrict__ small, const float* __restrict__ w, const float* __restrict__ bias,
@@ -388,14 +387,12 @@ int32_t launch_prep_frames(const void* src, int dtype, float scale, int cin, lon
 
 int32_t launch_deconv4_fwd(const float* small, const float* w, const float* bias, int batch, int ct,
                            float* logits_p, float* sigm, cudaStream_t stream) {
-    static const int nq = [] { const char* e = getenv("CPB_DECONV4_NQ"); return e && atoi(e) == 8 ? 8 : 4; }();
+    constexpr int nq = 4;                                          // 8 quads per thread measured 2x slower (254 registers)
     const long long npairs = (long long)batch * 40 * (80 / nq);     // groups of nq horizontally adjacent 2x2 output quads
     if (npairs == 0) return CPB_OK;
     const unsigned blocks = (unsigned)cdiv(npairs, 128);
-    if (ct == 3 && nq == 8) deconv4_fwd_kernel<3, 8><<<blocks, 128, 0, stream>>>(small, w, bias, npairs, logits_p, sigm);
-    else if (ct == 3) deconv4_fwd_kernel<3, 4><<<blocks, 128, 0, stream>>>(small, w, bias, npairs, logits_p, sigm);
-    else if (ct == 1 && nq == 8) deconv4_fwd_kernel<1, 8><<<blocks, 128, 0, stream>>>(small, w, bias, npairs, logits_p, sigm);
-    else if (ct == 1) deconv4_fwd_kernel<1, 4><<<blocks, 128, 0, stream>>>(small, w, bias, npairs, logits_p, sigm);
+    if (ct == 3) deconv4_fwd_kernel<3, nq><<<blocks, 128, 0, stream>>>(small, w, bias, npairs, logits_p, sigm);
+    else if (ct == 1) deconv4_fwd_kernel<1, nq><<<blocks, 128, 0, stream>>>(small, w, bias, npairs, logits_p, sigm);
     else CPB_REQUIRE(false, "deconv4: target_channels must be 1 or 3");
     CPB_LAUNCHED();
     return CPB_OK;

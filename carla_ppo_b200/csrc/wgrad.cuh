@@ -27,7 +27,7 @@ struct WgradParams {
     int I, J;              // output rows / cols (J multiple of the tile's BJ)
     int splits;
     long long m_per_split; // multiple of 16
-    int tc_variant;        // tensor-core path: timing decomposition (CPB_TC_DEBUG): 1 no MMA, 2 no stores, 4 no loads
+    int tc_variant;        // unused (kept for the cpb_debug_tc_wgrad signature)
 };
 
 // how many splits launch_wgrad will use for this problem (caller sizes `partial` with it)
