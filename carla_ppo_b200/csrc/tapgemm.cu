@@ -37,7 +37,8 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
     const int tx = tid % TXN;
     const int ty = tid / TXN;
     const int cls_id = blockIdx.z % p.nclass;
-    const int yb = blockIdx.z / p.nclass;
+    const int yb = (blockIdx.z / p.nclass) % p.ybatch;
+    const int ks = blockIdx.z / (p.nclass * p.ybatch);          // k-split index (ksplit > 1: dense layers with few rows)
     const TapClass& cls = p.cls[cls_id];
     const int Wo = cls.Wo;
     const int HoWo = cls.Ho * Wo;
@@ -99,8 +100,11 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-    const int nkb = cls.ntaps * (p.C / BK);
-    int ld_tap = 0, ld_c = 0;
+    // this CTA's share of the k-blocks (all of them unless the problem is k-split)
+    const int nkb_all = cls.ntaps * (p.C / BK);
+    const int kb_begin = (int)((long long)nkb_all * ks / p.ksplit);
+    const int nkb = (int)((long long)nkb_all * (ks + 1) / p.ksplit) - kb_begin;
+    int ld_tap = kb_begin / (p.C / BK), ld_c = (kb_begin % (p.C / BK)) * BK;
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
         if (s < nkb) {
@@ -157,6 +161,8 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
             bvals[g * 4 + q] = p.bias ? p.bias[yb * p.bias_ystride + n0 + tx * 4 + g * CSTEP + q] : 0.f;
 
     float* dst = p.dst + yb * p.dst_ystride;
+    const bool partial_out = p.ksplit > 1;                      // raw sums; ksplit_reduce adds bias / ReLU
+    if (partial_out) dst = p.kpartial + (long long)ks * p.kpartial_stride + yb * p.dst_ystride;
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
         const long long m = m0 + ty + i * RSTEP;
@@ -171,6 +177,11 @@ tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             float4 v;
+            if (partial_out) {
+                *reinterpret_cast<float4*>(dst + off + g * CSTEP) =
+                    make_float4(acc[i][g * 4 + 0], acc[i][g * 4 + 1], acc[i][g * 4 + 2], acc[i][g * 4 + 3]);
+                continue;
+            }
             v.x = acc[i][g * 4 + 0] + bvals[g * 4 + 0];
             v.y = acc[i][g * 4 + 1] + bvals[g * 4 + 1];
             v.z = acc[i][g * 4 + 2] + bvals[g * 4 + 2];
@@ -197,7 +208,7 @@ int32_t launch_cfg(const TapGemmParams& p, cudaStream_t stream) {
         if (m > max_m) max_m = m;
     }
     if (max_m == 0) return CPB_OK;
-    dim3 grid((unsigned)((max_m + BM - 1) / BM), (unsigned)(p.N / BN), (unsigned)(p.nclass * p.ybatch));
+    dim3 grid((unsigned)((max_m + BM - 1) / BM), (unsigned)(p.N / BN), (unsigned)(p.nclass * p.ybatch * p.ksplit));
     tapgemm_kernel<BM, BN, TM, TN, STAGES, MINB><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(p);
     CPB_LAUNCHED();
     return CPB_OK;
@@ -209,6 +220,28 @@ int32_t init_cfg() {
     CPB_CUDA(cudaFuncSetAttribute(tapgemm_kernel<BM, BN, TM, TN, STAGES, MINB>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     return CPB_OK;
+}
+
+// out[e] = epilogue( sum_s partial[s][e] ) for the k-split dense problems: e runs over [ybatch][rows][N]
+__global__ void ksplit_reduce_kernel(const float* __restrict__ partial, long long stride, int ksplit, long long total,
+                                     int N, long long ystride, const float* __restrict__ bias, long long bias_ystride,
+                                     int relu, float* __restrict__ dst) {
+    const long long e4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e4 * 4 >= total) return;
+    const long long e = e4 * 4;
+    float4 a = *reinterpret_cast<const float4*>(partial + e);
+    for (int s = 1; s < ksplit; ++s) {
+        const float4 v = *reinterpret_cast<const float4*>(partial + (long long)s * stride + e);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    if (bias != nullptr) {
+        const long long yb = ystride > 0 ? e / ystride : 0;
+        const int col = (int)((e - yb * ystride) % N);
+        const float4 b = *reinterpret_cast<const float4*>(bias + yb * bias_ystride + col);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+    *reinterpret_cast<float4*>(dst + e) = a;
 }
 
 }  // namespace
@@ -237,12 +270,35 @@ int32_t launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
         long long m = (long long)p.batch * p.cls[c].Ho * p.cls[c].Wo;
         if (m > max_m) max_m = m;
     }
+    CPB_REQUIRE(p.ksplit >= 1 && p.ksplit <= kMaxKSplit, "tapgemm: bad ksplit");
+    if (p.ksplit > 1) {
+        // dense layers with few rows and a long reduction (heads fwd, dense1 dgrad: K = 6144): a handful of CTAs
+        // walking 384 k-blocks each is latency bound at any batch size; split the reduction over gridDim.z
+        CPB_REQUIRE(p.nclass == 1 && p.cls[0].Ho == 1 && p.cls[0].Wo == 1 && p.mask == nullptr && p.kpartial != nullptr &&
+                    p.dst_pitch == p.N && p.N % 64 == 0, "tapgemm: k-split only for dense layers");
+        CPB_TRY((launch_cfg<CPB_TILE_D>(p, stream)));
+        const long long total = p.ybatch > 1 ? (long long)p.ybatch * p.dst_ystride : (long long)p.batch * p.N;
+        ksplit_reduce_kernel<<<cdiv(total / 4, 256), 256, 0, stream>>>(p.kpartial, p.kpartial_stride, p.ksplit, total, p.N,
+                                                                     p.ybatch > 1 ? p.dst_ystride : 0, p.bias, p.bias_ystride,
+                                                                     p.relu, p.dst);
+        CPB_LAUNCHED();
+        return CPB_OK;
+    }
     if (p.N % 128 == 0) return launch_cfg<CPB_TILE_A>(p, stream);
     if (p.N % 64 == 0) {
         if (max_m <= 16384) return launch_cfg<CPB_TILE_D>(p, stream);
         return launch_cfg<CPB_TILE_B>(p, stream);
     }
     return launch_cfg<CPB_TILE_C>(p, stream);
+}
+
+int tapgemm_pick_ksplit(int rows, int N, int ybatch, int K) {
+    // A function of K ONLY: the arithmetic a frame sees must not depend on the batch it is in (the B=4096 property
+    // test compares a batch with its quarters; a 1-ulp difference in the heads flips ReLUs downstream).
+    (void)rows; (void)N; (void)ybatch;
+    int s = kMaxKSplit;
+    while (s > 1 && (K / 16) / s < 24) --s;                     // keep >= 24 k-blocks per CTA
+    return s;
 }
 
 }  // namespace cpb

@@ -54,6 +54,9 @@ struct TapGemmParams {
     int nclass;           // 1 or 4
     int ybatch;           // independent problems sharing src (fused heads): 1 or 2
     long long w_ystride, bias_ystride, dst_ystride;
+    int ksplit;           // >= 1; > 1 (SIMT path, dense layers only): the reduction is split over gridDim.z into
+    float* kpartial;      // kpartial[ksplit][kpartial_stride] raw partial results, then reduced with the epilogue
+    long long kpartial_stride;
     // tensor-core path only: K-major per-tap [N][C] weight blocks, pre-split into hi / lo (tc_tapgemm.cu)
     const float* wk_hi;
     const float* wk_lo;
@@ -72,6 +75,9 @@ struct TapGemmParams {
 
 // Enqueue; picks the tile shape from N and the row count.
 int32_t launch_tapgemm(const TapGemmParams& p, cudaStream_t stream);
+constexpr int kMaxKSplit = 8;
+// k-split factor for a dense [rows x K] x [K x N] layer with N % 64 == 0 (1 = do not split)
+int tapgemm_pick_ksplit(int rows, int N, int ybatch, int K);
 // One-time opt-in for >48 KB dynamic shared memory (called from the API layer).
 int32_t tapgemm_init();
 

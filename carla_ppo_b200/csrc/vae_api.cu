@@ -172,6 +172,7 @@ struct VaePlan {
     float *gA, *gB, *gz, *gheads, *partial, *colsum;
     float* lo;          // lo plane scratch for tensor-core sources whose producer does not write one (small tensors)
     float *a1_lo, *a2_lo, *a3_lo, *b1_lo, *b2_lo, *gA_lo, *gB_lo;   // lo planes written by the producing kernels
+    float* ksplit;      // partial results of the k-split dense layers: kMaxKSplit x [2, B, z]
     int64_t bytes;
     bool ok;
 };
@@ -214,6 +215,7 @@ static VaePlan make_plan(void* ws, int64_t ws_bytes, int B, int ct, int z, int m
     p.a4 = a.take<float>(b * FEAT);
     p.heads = a.take<float>(2 * b * z);
     p.lo = a.take<float>(b * FEAT);
+    p.ksplit = a.take<float>((int64_t)kMaxKSplit * 2 * b * z);
     p.a1_lo = a.take<float>(b * H1 * W1 * C1);
     p.a2_lo = a.take<float>(b * H2 * W2 * C2);
     p.a3_lo = a.take<float>(b * H3 * W3 * C3);
@@ -255,6 +257,7 @@ static TapGemmParams base_params() {
     memset(&p, 0, sizeof(p));
     p.nclass = 1;
     p.ybatch = 1;
+    p.ksplit = 1;
     return p;
 }
 
@@ -504,6 +507,10 @@ static int32_t run_encoder(const VaePlan& pl, const VaeLayout& L, const cpb_vae_
     p.w_ystride = L.off[T_LOGVAR_K] - L.off[T_MEAN_K];
     p.bias_ystride = L.off[T_LOGVAR_B] - L.off[T_MEAN_B];
     p.dst_ystride = (long long)B * pl.z;
+    if (pl.z % 64 == 0) {
+        p.ksplit = tapgemm_pick_ksplit(B, pl.z, 2, FEAT);
+        p.kpartial = pl.ksplit; p.kpartial_stride = 2LL * B * pl.z;
+    }
     return tg("heads.fwd", p, s);
 }
 
@@ -598,6 +605,10 @@ static int32_t run_backward(const VaePlan& pl, const VaeLayout& L, const cpb_vae
     CPB_TRY(run_dense_wgrad("dense1.wgrad", pl.zbuf, z, pl.gB, B, FEAT, pl.partial, grads + L.off[T_DENSE1_K], s));
     CPB_TRY(launch_colsum(pl.gB, B, FEAT, FEAT, grads + L.off[T_DENSE1_B], cs, s));
     p = dense_problem(pl.gB, B, FEAT, pl.relayout + pl.rl.dense1T, z, nullptr, nullptr, pl.gz, 0);
+    if (z % 64 == 0) {
+        p.ksplit = tapgemm_pick_ksplit(B, z, 1, FEAT);
+        p.kpartial = pl.ksplit; p.kpartial_stride = (long long)B * z;
+    }
     CPB_TRY(tg("dense1.dgrad", p, s));
     // ---- sampling + KL
     CPB_TRY(launch_reparam_bwd(pl.heads, eps, pl.gz, pl.kl_active, B, z, cfg->beta * cfg->loss_scale / (float)B,
