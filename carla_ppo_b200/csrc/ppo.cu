@@ -75,7 +75,7 @@ struct GemmJob {
 };
 
 struct GemmBatch {
-    GemmJob job[2];
+    GemmJob job[6];       // independent GEMMs of one launch (blockIdx.z); all with the same gather mode
 };
 
 template <int GATHER>
@@ -578,17 +578,16 @@ int32_t run_loss_grad(const cpb_ppo_config* c, const PpoLayout& L, const PpoPlan
                                          c->entropy_scale, grads + L.off[P_LOGSTD], metrics);
     CPB_LAUNCHED();
     GemmBatch gb;
-    // head weights: gWm[H2,A] = h2p^T dpre, gbm = colsum(dpre); gWv[H2,1] = h2v^T dv, gbv = sum(dv)
-    gb.job[0] = bwd_weight_job(h2p, nullptr, B, H2, pl.dpre, A, grads + L.off[P_WM], grads + L.off[P_BM]);
-    gb.job[1] = bwd_weight_job(h2v, nullptr, B, H2, pl.dv, 1, grads + L.off[P_WV], grads + L.off[P_BV]);
-    CPB_TRY(launch_small_gemm(gb, 2, s));
-    // layer 2 of both trunks
+    // everything that only needs the head kernel's outputs goes into ONE launch (6 independent GEMMs):
+    // head weights gWm[H2,A] = h2p^T dpre, gbm = colsum(dpre); gWv[H2,1] = h2v^T dv, gbv = sum(dv);
+    // layer-2 weights of both trunks; layer-2 data gradients of both trunks
     gb.job[0] = bwd_weight_job(h1p, nullptr, B, H1, dh2p, H2, grads + L.off[P_W2], grads + L.off[P_B2]);
     gb.job[1] = bwd_weight_job(h1v, nullptr, B, H1, dh2v, H2, grads + L.off[P_V2], grads + L.off[P_VB2]);
-    CPB_TRY(launch_small_gemm(gb, 2, s));
-    gb.job[0] = bwd_data_job(dh2p, B, H2, params + L.off[P_W2], H1, h1p, dh1p);
-    gb.job[1] = bwd_data_job(dh2v, B, H2, params + L.off[P_V2], H1, h1v, dh1v);
-    CPB_TRY(launch_small_gemm(gb, 2, s));
+    gb.job[2] = bwd_data_job(dh2p, B, H2, params + L.off[P_W2], H1, h1p, dh1p);
+    gb.job[3] = bwd_data_job(dh2v, B, H2, params + L.off[P_V2], H1, h1v, dh1v);
+    gb.job[4] = bwd_weight_job(h2p, nullptr, B, H2, pl.dpre, A, grads + L.off[P_WM], grads + L.off[P_BM]);
+    gb.job[5] = bwd_weight_job(h2v, nullptr, B, H2, pl.dv, 1, grads + L.off[P_WV], grads + L.off[P_BV]);
+    CPB_TRY(launch_small_gemm(gb, 6, s));
     // layer 1 of both trunks
     gb.job[0] = bwd_weight_job(states, idx, B, S, dh1p, H1, grads + L.off[P_W1], grads + L.off[P_B1]);
     gb.job[1] = bwd_weight_job(states, idx, B, S, dh1v, H1, grads + L.off[P_V1], grads + L.off[P_VB1]);
