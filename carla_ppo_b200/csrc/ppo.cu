@@ -43,7 +43,7 @@ PpoLayout make_ppo_layout(const cpb_ppo_config* c) {
 // small tile GEMM: C[M,N] (+)= A'[M,K] * B'[K,N], 32x32 tile, 64 threads, 4x4 per thread
 // ---------------------------------------------------------------------------------------------
 constexpr int TS = 32;   // tile edge
-constexpr int TK = 32;   // reduction chunk (one global round trip per chunk: keep the chunk count low)
+constexpr int TK = 64;   // reduction chunk (one global round trip per chunk: keep the chunk count low)
 
 // operand access descriptors (element (o, r) = output index o, reduction index r)
 struct Operand {
