@@ -4,24 +4,28 @@
 //     a*b  ~=  a_hi*b_hi + a_lo*b_hi + a_hi*b_lo ,   x_hi = x with the 13 low mantissa bits cleared,  x_lo = x - x_hi
 //
 // so that results stay fp32-accurate (relative error ~1e-6; a single TF32 pass gives ~3e-4 and would break the
-// 1e-5 parity bar).  Operands are staged in shared memory in the UMMA canonical K-major SWIZZLE_128B layout
-// (rows of 32 floats = 128 B, 8-row groups of 1024 B, 16-byte chunk index XOR row%8):
-//   * A (activations, gathered rows) : LDG.128 -> registers -> hi/lo split -> 2 x STS.128 (swizzled)
-//   * B (weights)                    : pre-split, K-major copies written once per step by tc_weights_kernel,
-//                                      copied with cp.async (no register staging)
-// One elected thread issues 12 MMAs per 32-wide k-block (4 k-steps x 3 products); tcgen05.commit arrives on the
-// stage's mbarrier when they retire, which frees the stage for the loaders.
+// 1e-5 parity bar).  The tensor core itself ignores the 13 low mantissa bits of a TF32 operand, so the raw fp32
+// tensor IS x_hi; x_lo is a second fp32 plane (written by the producing kernel's epilogue, or by lo_plane_kernel).
+// Operands are staged in shared memory in the UMMA canonical K-major SWIZZLE_128B layout (rows of 32 floats =
+// 128 B, 8-row groups of 1024 B, 16-byte chunk index XOR row%8):
+//   * A (activations, gathered rows) : cp.async 16 B per thread and row from the raw tensor (hi) and its lo plane,
+//                                      zero-filled outside the image, completion counted on the stage's mbarrier;
+//   * B (weights)                    : stored by tc_weights_kernel as ready-made swizzled tile images [hi | lo]; one
+//                                      cp.async.bulk per k-block (optionally multicast to the CTAs of a cluster).
+// Persistent, warp-specialised kernel (see tc_tapgemm_kernel): loader warps, one weight-producer lane, one MMA-issuer
+// lane (8 MMAs per 32-wide k-block: [main | cross] += a_hi x [b_hi | b_lo] with N = 2*BN, cross += a_lo x b_hi),
+// eight drain / epilogue warps.
 //
 // Accumulation.  The tensor core adds into its fp32 accumulator with round-toward-zero, which shrinks a long
 // running sum systematically (measured on B200: relative bias -6.5e-9 x K, i.e. -7e-6 at K=1024, -2.6e-5 at
 // K=4096; scripts/diag_tc.py).  Two measures bring this back to fp32-FMA level:
-//   * the two cross terms (2^-11 of the main term) accumulate in their OWN TMEM tile, so they no longer
-//     re-truncate the large accumulator twice per k-step;
-//   * accumulation inside TMEM only runs over chunks of 128 k (4 k-blocks, 16 + 32 MMAs) into two ping-pong
-//     (main | cross) buffers; each finished chunk is drained with tcgen05.ld and added to per-thread fp32
-//     REGISTER accumulators (round-to-nearest).  The drain of chunk j is issued one chunk late, when its MMAs
-//     have long retired, so it never stalls the loaders.
-// The register accumulators feed the bias / ReLU / ReLU-mask epilogue directly.
+//   * the cross terms (2^-11 of the main term) accumulate in their OWN TMEM columns, so they do not re-truncate the
+//     large accumulator;
+//   * accumulation inside TMEM only runs over chunks of 128 k (4 k-blocks) into two ping-pong (main | cross)
+//     buffers; each finished chunk is drained with tcgen05.ld and added to per-thread fp32 REGISTER accumulators
+//     (round-to-nearest) by the drain warps while the tensor core works on the next chunk.
+// The register accumulators feed the bias / ReLU / ReLU-mask epilogue directly; the epilogue also writes the lo plane
+// of its output when the consumer is another tensor-core layer.
 #include "tapgemm.cuh"
 #include "tc_common.cuh"
 

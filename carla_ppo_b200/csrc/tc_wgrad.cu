@@ -2,17 +2,19 @@
 //
 //   gw[i, j] = sum_{m}  big[row(m) + tap_off[i / run] + i % run] * small[m * J + j]        (same contract as wgrad.cu)
 //
-// as D[128 x BN] += A^T B with the REDUCTION index m on the MMA K axis.  Both operands are activations / gradients
-// (nothing can be pre-split), and in NHWC memory the channel index -- not m -- is contiguous, while the tensor
-// core wants K-major tiles (for 32-bit operands the MN-major alternative is the special SWIZZLE_128B_BASE32B
-// layout).  The loader therefore transposes 4x4 blocks in registers: a thread reads the float4 of 4 channels at
-// 4 consecutive reduction positions (4 x LDG.128), regroups them into 4 vectors "one channel x 4 positions",
-// splits them into TF32 hi / lo parts and writes each as ONE 16-byte chunk of the K-major SWIZZLE_128B tile
-// (8 STS.128).  Lanes of a quarter-warp own 2 adjacent channel groups x 4 position blocks, so the swizzled chunk
-// index (block ^ row%8) spreads them over all banks (conflict-free), and a warp's loads cover 4 rows x 128
-// contiguous bytes (fully coalesced).  MMA issue, the 3xTF32 products, the separate cross-term tile and the chunked
-// drain into fp32 register accumulators are those of tc_tapgemm.cu.  Each (i-tile, j-tile, split) CTA writes its
-// partial [128 x BN] block; reduce_partials() sums the splits in a fixed order (deterministic).
+// as D[128 x BN] += A^T B with the REDUCTION index m on the MMA K axis.  In NHWC memory the channel index -- not m --
+// is contiguous, while the tensor core wants K-major tiles (for 32-bit operands the MN-major alternative is the
+// special SWIZZLE_128B_BASE32B layout), so unlike tc_tapgemm.cu this kernel keeps a register path: a loader thread
+// reads the float4 of 4 channels at 4 consecutive reduction positions (4 x LDG.128), regroups them into 4 vectors
+// "one channel x 4 positions" (4x4 register transpose), splits them into TF32 hi / lo parts and writes each as ONE
+// 16-byte chunk of the K-major SWIZZLE_128B tile (8 STS.128).  A quarter-warp covers 8 consecutive channel groups of
+// ONE position (a contiguous 128-byte line per LDG.128); the tile rows are permuted (channel 4*cg + c lives in row
+// 32*c + cg) so that the swizzled stores stay conflict-free, and the accumulator rows / columns are un-permuted
+// when the partial is stored.  Warps 0-7 load A (and drain the accumulator chunks), warps 8-11 load B, warp 12
+// issues the MMAs; two k-blocks are in flight per loader thread; the position cursor advances without divisions.
+// 3xTF32 products, the separate cross-term tile and the chunked drain into fp32 register accumulators are those of
+// tc_tapgemm.cu.  Each (i-tile, j-tile, split) CTA of the single split-K wave writes its partial [128 x BN] block;
+// reduce_partials() sums the splits in a fixed order (deterministic).
 #include "tc_common.cuh"
 #include "wgrad.cuh"
 
