@@ -213,6 +213,11 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    # the contract is ONE JSON line on stdout: anything native libraries print meanwhile (NCCL's version banner, with
+    # NCCL_DEBUG=INFO its whole log) is sent to stderr by pointing fd 1 at fd 2 until the line is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
@@ -331,7 +336,10 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if out is not None:
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(out), flush=True)
+        os.dup2(2, 1)
 
 
 # ============================================================================================= reference arm
