@@ -52,6 +52,7 @@ PROTOTYPES = {
     "cpb_vae_forward": (_i32, [_VC, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _i64, _P]),
     "cpb_vae_loss_grad": (_i32, [_VC, _P, _P, _P, _P, _P, _P, _P, _P, _i64, _P]),
     "cpb_adam_apply": (_i32, [_P, _P, _P, _P, _i64, _P, _f32, _P, _f32, _f32, _f32, _P]),
+    "cpb_adam_apply_guarded": (_i32, [_P, _P, _P, _P, _i64, _P, _f32, _P, _f32, _f32, _f32, _P, _P]),
     "cpb_vae_train_step": (_i32, [_VC, _P, _P, _P, _P, _P, _f32, _P, _P, _P, _P, _P, _P, _i64, _P]),
     "cpb_vae_staging_bytes": (_i64, [_VC]),
     "cpb_vae_train_step_host": (_i32, [_VC, _P, _P, _P, _P, _P, _f32, _P, _P, _P, _P, _P, _P, _i64, _P, _i64, _P]),
@@ -116,9 +117,12 @@ def ptr(t) -> Optional[int]:
     raise TypeError(type(t))
 
 
-def current_stream_handle() -> int:
+def current_stream_handle(device=None) -> int:
+    """cudaStream_t of torch's current stream ON `device` (default: the current device).  The library launches on the
+    CUDA device that is current at call time, so callers holding a device wrap the call in ``torch.cuda.device(dev)``
+    and pass the same device here."""
     import torch
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 def require_cuda():

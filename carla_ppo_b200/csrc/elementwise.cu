@@ -182,8 +182,10 @@ __device__ __forceinline__ void loss_elem(float x, float y, float& val, float& d
 
 template <int LOSS, int CT>
 __global__ void __launch_bounds__(256)
-recon_loss_kernel(const float4* __restrict__ logits_p, const float4* __restrict__ target_p, int npix, float gscale,
-                  float* __restrict__ frame_loss, float4* __restrict__ dlogits_p) {
+recon_loss_kernel(const float4* logits_p, const float4* __restrict__ target_p, int npix, float gscale,
+                  float* __restrict__ frame_loss, float4* dlogits_p) {
+    // logits_p and dlogits_p MAY ALIAS (the training path overwrites the logits with d loss / d logits in place): neither
+    // is __restrict__, each element is read before it is written by the same thread.
     const long long base = (long long)blockIdx.x * npix;
     float sum = 0.f;
     for (int p = threadIdx.x; p < npix; p += blockDim.x) {
@@ -338,9 +340,11 @@ __global__ void relayout_kernel(const float* __restrict__ params, float* __restr
 // ------------------------------------------------------------------------------------------
 __global__ void adam_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
                             float4* __restrict__ v, long long n4, const float* __restrict__ powers, float lr,
-                            const float* __restrict__ lr_dev, float beta1, float beta2, float epsilon) {
+                            const float* __restrict__ lr_dev, float beta1, float beta2, float epsilon,
+                            const uint32_t* __restrict__ guard) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
+    if (guard != nullptr && guard[0] != 0u) return;     // verify_range tripped: the reference's tf.Assert aborts BEFORE the update
     const float lr_t = lr_dev != nullptr ? lr_dev[0] : lr;
     const float alpha = lr_t * sqrtf(1.f - powers[1]) / (1.f - powers[0]);
     const float omb1 = 1.f - beta1, omb2 = 1.f - beta2;
@@ -354,7 +358,8 @@ __global__ void adam_kernel(float4* __restrict__ p, const float4* __restrict__ g
     m[i] = mv; v[i] = vv; p[i] = pv;
 }
 
-__global__ void adam_powers_kernel(float* powers, float beta1, float beta2) {
+__global__ void adam_powers_kernel(float* powers, float beta1, float beta2, const uint32_t* __restrict__ guard) {
+    if (guard != nullptr && guard[0] != 0u) return;
     powers[0] *= beta1;
     powers[1] *= beta2;
 }
@@ -476,13 +481,14 @@ int32_t launch_relayout(const float* params, float* dst, const RelayoutTable& ta
 }
 
 int32_t launch_adam(float* params, const float* grads, float* m, float* v, long long n, float* powers,
-                    float lr, const float* lr_dev, float beta1, float beta2, float epsilon, cudaStream_t stream) {
+                    float lr, const float* lr_dev, float beta1, float beta2, float epsilon, cudaStream_t stream,
+                    const void* guard) {
     CPB_REQUIRE(n % 4 == 0, "adam: buffer length %lld is not a multiple of 4", n);
     if (n == 0) return CPB_OK;
     adam_kernel<<<cdiv(n / 4, 256), 256, 0, stream>>>((float4*)params, (const float4*)grads, (float4*)m, (float4*)v,
-                                                      n / 4, powers, lr, lr_dev, beta1, beta2, epsilon);
+                                                      n / 4, powers, lr, lr_dev, beta1, beta2, epsilon, (const uint32_t*)guard);
     CPB_LAUNCHED();
-    adam_powers_kernel<<<1, 1, 0, stream>>>(powers, beta1, beta2);
+    adam_powers_kernel<<<1, 1, 0, stream>>>(powers, beta1, beta2, (const uint32_t*)guard);
     CPB_LAUNCHED();
     return CPB_OK;
 }

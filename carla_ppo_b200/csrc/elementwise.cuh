@@ -63,8 +63,10 @@ struct RelayoutTable {
 };
 int32_t launch_relayout(const float* params, float* dst, const RelayoutTable& table, cudaStream_t stream);
 
+// guard (nullable, device, one 32-bit word): when its bits are non-zero the update is skipped entirely (verify_range)
 int32_t launch_adam(float* params, const float* grads, float* m, float* v, long long n, float* powers,
-                    float lr, const float* lr_dev, float beta1, float beta2, float epsilon, cudaStream_t stream);
+                    float lr, const float* lr_dev, float beta1, float beta2, float epsilon, cudaStream_t stream,
+                    const void* guard = nullptr);
 
 int32_t launch_fill_zero(float* p, long long n, cudaStream_t stream);
 

@@ -691,7 +691,8 @@ int32_t cpb_ppo_learn(const cpb_ppo_config* cfg, float* params, float* params_ol
     CPB_REQUIRE(T >= 1 && batch_size >= 1 && num_epochs >= 0, "ppo_learn: bad sizes");
     CPB_PPO_PLAN(batch_size < T ? batch_size : T, T);
     CPB_REQUIRE(params && params_old && grads && adam_m && adam_v && adam_powers && lr_dev && states && actions &&
-                rewards && values && dones && perms, "ppo_learn: NULL pointer");
+                rewards && values && dones, "ppo_learn: NULL pointer");
+    CPB_REQUIRE(perms != nullptr || num_epochs == 0, "ppo_learn: perms is NULL");
     // GAE, returns, normalised advantages (float64), rounded to float32 like the reference's feed
     gae_kernel<<<1, 1024, 0, s>>>(rewards, values, bootstrap_value, dones, T, gamma, lam, nullptr, nullptr, nullptr,
                                   pl.ret32, pl.adv32, pl.gae_scratch);

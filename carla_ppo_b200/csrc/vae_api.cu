@@ -43,16 +43,26 @@ void profile_end(cudaStream_t s) {
 }
 
 int g_math_mode = 1;   // 0: fp32 SIMT everywhere; 1: 3xTF32 tcgen05 for the dense conv/deconv layers
-static std::once_flag g_init_once;
-static int32_t g_init_status = CPB_OK;
+// Per-device one-time setup (cudaFuncSetAttribute for > 48 KB dynamic shared memory and the co-resident cluster counts
+// of the persistent kernels are PER DEVICE): keyed by cudaGetDevice() so that a process driving several GPUs works.
+constexpr int kMaxDevices = 64;
+static std::mutex g_init_mutex;
+static int g_init_done[kMaxDevices];     // 0: not yet, 1: ok, 2: failed
+static int32_t g_init_status[kMaxDevices];
 int32_t ensure_init() {
-    std::call_once(g_init_once, [] {
-        g_init_status = tapgemm_init();
-        if (g_init_status == CPB_OK) g_init_status = wgrad_init();
-        if (g_init_status == CPB_OK) g_init_status = tc_tapgemm_init();
-        if (g_init_status == CPB_OK) g_init_status = tc_wgrad_init();
-    });
-    return g_init_status;
+    int dev = 0;
+    CPB_CUDA(cudaGetDevice(&dev));
+    CPB_REQUIRE(dev >= 0 && dev < kMaxDevices, "device ordinal %d out of range", dev);
+    std::lock_guard<std::mutex> lock(g_init_mutex);
+    if (g_init_done[dev] == 0) {
+        int32_t st = tapgemm_init();
+        if (st == CPB_OK) st = wgrad_init();
+        if (st == CPB_OK) st = tc_tapgemm_init();
+        if (st == CPB_OK) st = tc_wgrad_init();
+        g_init_status[dev] = st;
+        g_init_done[dev] = st == CPB_OK ? 1 : 2;
+    }
+    return g_init_status[dev];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -671,7 +681,8 @@ void cpb_reset_launch_count(void) { cpb::g_launches = 0; }
 int32_t cpb_debug_vae_buffer_offsets(int32_t batch, int32_t ct, int32_t z, int32_t mode, int64_t* offsets, int32_t capacity) {
     char* base = (char*)4096;   // fake non-null base: only differences are used
     VaePlan pl = make_plan(base, (int64_t)1 << 60, batch, ct, z, mode);
-    const float* ptrs[] = {pl.xp, pl.a1, pl.a2, pl.a3, pl.a4, pl.heads, pl.zbuf, pl.d1, pl.b1, pl.b2, pl.b3, pl.logits_p, pl.gA, pl.gB};
+    const float* ptrs[] = {pl.xp, pl.a1, pl.a2, pl.a3, pl.a4, pl.heads, pl.zbuf, pl.d1, pl.b1, pl.b2, pl.b3, pl.logits_p, pl.gA, pl.gB,
+                           pl.frame_loss, pl.kl_rows};
     const int n = (int)(sizeof(ptrs) / sizeof(ptrs[0]));
     for (int i = 0; i < n && i < capacity; ++i) offsets[i] = ptrs[i] ? (int64_t)((const char*)ptrs[i] - base) : -1;
     return n;
@@ -837,12 +848,21 @@ int32_t cpb_adam_apply(float* params, const float* grads, float* m, float* v, in
     return launch_adam(params, grads, m, v, n, powers, lr, lr_dev, beta1, beta2, epsilon, (cudaStream_t)stream);
 }
 
+int32_t cpb_adam_apply_guarded(float* params, const float* grads, float* m, float* v, int64_t n, float* powers, float lr,
+                               const float* lr_dev, float beta1, float beta2, float epsilon, const void* guard, void* stream) {
+    CPB_REQUIRE(params && grads && m && v && powers, "adam: NULL pointer");
+    ProfScope prof("adam", (cudaStream_t)stream);
+    return launch_adam(params, grads, m, v, n, powers, lr, lr_dev, beta1, beta2, epsilon, (cudaStream_t)stream, guard);
+}
+
 int32_t cpb_vae_train_step(const cpb_vae_config* cfg, float* params, float* grads, float* adam_m, float* adam_v,
                            float* adam_powers, float lr, const void* source, const void* target, const float* eps,
                            float* losses, int32_t* flags, void* workspace, int64_t workspace_bytes, void* stream) {
     CPB_TRY(cpb_vae_loss_grad(cfg, params, source, target, eps, grads, losses, flags, workspace, workspace_bytes, stream));
     VaeLayout L = make_layout(cfg->target_channels, cfg->z_dim);
-    return cpb_adam_apply(params, grads, adam_m, adam_v, L.total, adam_powers, lr, nullptr, 0.9f, 0.999f, 1e-8f, stream);
+    // verify_range (vae/models.py:24-30, 89-90) is a tf.Assert the train op depends on: an out-of-range batch aborts the
+    // reference's sess.run BEFORE ApplyAdam.  Same here: the update is skipped on the device when a flag bit is set.
+    return cpb_adam_apply_guarded(params, grads, adam_m, adam_v, L.total, adam_powers, lr, nullptr, 0.9f, 0.999f, 1e-8f, flags, stream);
 }
 
 static int64_t frame_bytes(int dtype, int channels) {

@@ -82,6 +82,9 @@ class PPO:
         self._torch, self._libh = torch, lib
         if self._device is None:
             self._device = torch.device("cuda", torch.cuda.current_device())
+        self._device = torch.device(self._device)
+        if self._device.index is None:
+            self._device = torch.device("cuda", torch.cuda.current_device())
         dev = self._device
         self._c = self._cfg()
         n = lib.cpb_ppo_num_tensors()
@@ -178,6 +181,14 @@ class PPO:
         if self.sess is None:
             raise CpbError("init_session() has not been called")
 
+    def _stream(self):
+        return _lib.current_stream_handle(self._device)
+
+    def _call(self, name, *args):
+        """C entry point with this model's device current (the library launches on the CURRENT CUDA device)."""
+        with self._torch.cuda.device(self._device):
+            return _lib.check(getattr(self._libh, name)(*args), name)
+
     def _workspace(self, max_batch, horizon=0):
         need = self._libh.cpb_ppo_workspace_bytes(C.byref(self._c), int(max_batch), int(horizon))
         _lib.check(need, "cpb_ppo_workspace_bytes")
@@ -194,7 +205,9 @@ class PPO:
         return torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np_dtype))).to(self._device)
 
     # ------------------------------------------------------------------ checkpoints
-    def save(self):
+    def save(self, tf_format=False):
+        """.npz checkpoint + ``checkpoint`` state file (ppo.py:202-205); ``tf_format=True`` writes a TF-V2 tensor bundle
+        with the reference's variable names instead (readable by the reference's ``saver.restore``)."""
         self._require_session()
         step = int(self.episode_counter)
         prefix = os.path.join(self.checkpoint_dir, "model.ckpt-%d" % step)
@@ -212,7 +225,11 @@ class PPO:
         blob["episode_counter"] = np.int32(self.episode_counter)
         blob["train_step_counter"] = np.int32(self.train_step_counter)
         blob["predict_step_counter"] = np.int32(self.predict_step_counter)
-        np.savez(prefix + ".npz", **blob)
+        if tf_format:
+            from .tf_bundle import write_bundle
+            write_bundle(prefix, {k: np.asarray(v) for k, v in blob.items()})
+        else:
+            np.savez(prefix + ".npz", **blob)
         state = os.path.join(self.checkpoint_dir, "checkpoint")
         kept = []
         if os.path.isfile(state):
@@ -221,10 +238,11 @@ class PPO:
         name = os.path.basename(prefix)
         kept = [k for k in kept if k != name] + [name]
         for old in kept[:-5]:
-            try:
-                os.remove(os.path.join(self.checkpoint_dir, old + ".npz"))
-            except OSError:
-                pass
+            for ext in (".npz", ".index", ".data-00000-of-00001"):
+                try:
+                    os.remove(os.path.join(self.checkpoint_dir, old + ext))
+                except OSError:
+                    pass
         with open(state, "w") as f:
             f.write('model_checkpoint_path: "%s"\n' % name)
             for k in kept[-5:]:
@@ -288,11 +306,11 @@ class PPO:
             raise ValueError("train(): inconsistent batch sizes")
         metrics = torch.empty(5, dtype=torch.float32, device=self._device)
         ws = self._workspace(b)
-        _lib.check(self._libh.cpb_ppo_train_step(
+        self._call("cpb_ppo_train_step", 
             C.byref(self._c), _lib.ptr(self.params), _lib.ptr(self.params_old), _lib.ptr(self.grads),
             _lib.ptr(self.adam_m), _lib.ptr(self.adam_v), _lib.ptr(self.adam_powers), _lib.ptr(self._lr_dev),
             _lib.ptr(s), _lib.ptr(a), _lib.ptr(r), _lib.ptr(adv), None, b, _lib.ptr(metrics), _lib.ptr(ws),
-            ws.numel(), _lib.current_stream_handle()), "cpb_ppo_train_step")
+            ws.numel(), self._stream())
         self._pending_metrics.append(metrics)
         self.train_step_counter += 1
         return metrics
@@ -308,10 +326,10 @@ class PPO:
         b = s.shape[0]
         metrics = torch.empty(5, dtype=torch.float32, device=self._device)
         ws = self._workspace(b)
-        _lib.check(self._libh.cpb_ppo_loss_grad(
+        self._call("cpb_ppo_loss_grad", 
             C.byref(self._c), _lib.ptr(self.params), _lib.ptr(self.params_old), _lib.ptr(s), _lib.ptr(a), _lib.ptr(r),
             _lib.ptr(adv), None, b, _lib.ptr(self.grads), _lib.ptr(metrics), _lib.ptr(ws), ws.numel(),
-            _lib.current_stream_handle()), "cpb_ppo_loss_grad")
+            self._stream())
         return metrics.cpu().numpy(), self.get_grads()
 
     def predict(self, input_states, greedy=False, write_to_summary=False, noise=None):
@@ -333,9 +351,9 @@ class PPO:
         nz = None if greedy else dev[b * self.state_dim:]
         out = torch.empty(b * (a_dim + 1), dtype=torch.float32, device=self._device)
         ws = self._workspace(b)
-        _lib.check(self._libh.cpb_ppo_forward(C.byref(self._c), _lib.ptr(self.params), _lib.ptr(s), b, _lib.ptr(nz),
+        self._call("cpb_ppo_forward", C.byref(self._c), _lib.ptr(self.params), _lib.ptr(s), b, _lib.ptr(nz),
                                               _lib.ptr(out), _lib.ptr(out[b * a_dim:]), _lib.ptr(ws), ws.numel(),
-                                              _lib.current_stream_handle()), "cpb_ppo_forward")
+                                              self._stream())
         host = out.cpu().numpy()
         action, value = host[:b * a_dim].reshape(b, a_dim), host[b * a_dim:]
         if write_to_summary:
@@ -368,23 +386,25 @@ class PPO:
         d = self._dev(np.asarray(dones, dtype=np.float64) if not isinstance(dones, torch.Tensor) else dones, torch.float64).reshape(t_len)
         if perms is None:
             perms = np.stack([np.random.permutation(t_len) for _ in range(num_epochs)]) if num_epochs else np.zeros((0, t_len))
-        if isinstance(perms, torch.Tensor):
+        if num_epochs == 0:
+            p = None                       # nothing to index: the C entry accepts perms == NULL for zero epochs
+        elif isinstance(perms, torch.Tensor):
             p = perms.to(self._device, torch.int32).reshape(num_epochs, t_len).contiguous()
         else:
             p = self._dev(np.asarray(perms).reshape(num_epochs, t_len), torch.int32)
         nmb = -(-t_len // batch_size)
         metrics = torch.empty(max(num_epochs * nmb, 1), 5, dtype=torch.float32, device=self._device)
         ws = self._workspace(min(batch_size, t_len), t_len)
-        _lib.check(self._libh.cpb_ppo_learn(
+        self._call("cpb_ppo_learn", 
             C.byref(self._c), _lib.ptr(self.params), _lib.ptr(self.params_old), _lib.ptr(self.grads),
             _lib.ptr(self.adam_m), _lib.ptr(self.adam_v), _lib.ptr(self.adam_powers), _lib.ptr(self._lr_dev),
             _lib.ptr(s), _lib.ptr(a), _lib.ptr(r), _lib.ptr(v), float(last_value), _lib.ptr(d), t_len, float(gamma),
             float(lam), int(num_epochs), int(batch_size), _lib.ptr(p), _lib.ptr(metrics), _lib.ptr(ws), ws.numel(),
-            _lib.current_stream_handle()), "cpb_ppo_learn")
+            self._stream())
         self.train_step_counter += num_epochs * nmb
         self._pending_metrics.append(metrics[:num_epochs * nmb])
         if return_metrics:
-            return metrics[:num_epochs * nmb].cpu().numpy()
+            return metrics[:num_epochs * nmb].cpu().numpy().reshape(num_epochs * nmb, 5)
         return None
 
     # ------------------------------------------------------------------ counters / summaries

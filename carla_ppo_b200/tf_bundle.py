@@ -165,3 +165,145 @@ def latest_checkpoint(checkpoint_dir: str) -> Optional[str]:
     if not os.path.isabs(path):
         path = os.path.join(checkpoint_dir, path)
     return path if os.path.isfile(path + ".index") else None
+
+
+# ----------------------------------------------------------------------------- writer
+_CRC_TABLE = None
+
+
+def crc32c(data: bytes, crc: int = 0) -> int:
+    """CRC-32C (Castagnoli), the checksum TF stores per tensor and per index block."""
+    global _CRC_TABLE
+    if _CRC_TABLE is None:
+        tab = []
+        for i in range(256):
+            c = i
+            for _ in range(8):
+                c = (c >> 1) ^ 0x82F63B78 if c & 1 else c >> 1
+            tab.append(c)
+        _CRC_TABLE = tab
+    tab = _CRC_TABLE
+    crc ^= 0xFFFFFFFF
+    for b in memoryview(data).cast("B"):
+        crc = tab[(crc ^ b) & 0xFF] ^ (crc >> 8)
+    return crc ^ 0xFFFFFFFF
+
+
+def masked_crc32c(data: bytes) -> int:
+    """The rotated + offset form LevelDB / TF store ("masked" CRC)."""
+    c = crc32c(data)
+    return (((c >> 15) | (c << 17)) + 0xA282EAD8) & 0xFFFFFFFF
+
+
+def _enc_varint(v: int) -> bytes:
+    out = bytearray()
+    while True:
+        b = v & 0x7F
+        v >>= 7
+        if v:
+            out.append(b | 0x80)
+        else:
+            out.append(b)
+            return bytes(out)
+
+
+def _field(num: int, wire: int, payload: bytes) -> bytes:
+    tag = _enc_varint((num << 3) | wire)
+    if wire == 2:
+        return tag + _enc_varint(len(payload)) + payload
+    return tag + payload
+
+
+def _block(entries) -> bytes:
+    """One uncompressed table block: every entry is its own restart point (no prefix sharing)."""
+    body = bytearray()
+    restarts = []
+    for key, value in entries:
+        restarts.append(len(body))
+        body += _enc_varint(0) + _enc_varint(len(key)) + _enc_varint(len(value)) + key + value
+    for r in restarts:
+        body += struct.pack("<I", r)
+    body += struct.pack("<I", len(restarts))
+    return bytes(body)
+
+
+_DTYPE_ENUM = {np.dtype("<f4"): 1, np.dtype("<f8"): 2, np.dtype("<i4"): 3, np.dtype("<i8"): 9}
+
+
+def write_bundle(prefix: str, tensors: Dict[str, np.ndarray]) -> None:
+    """Writes ``<prefix>.index`` + ``<prefix>.data-00000-of-00001`` in the TF-V2 tensor-bundle format described at the
+    top of this file (one shard, one uncompressed data block, per-tensor crc32c), i.e. what ``tf.train.Saver.save``
+    produces for the reference (vae/models.py:172-175, ppo.py:202-205) -- so a checkpoint written by this build can be
+    restored by the reference's own ``saver.restore`` and vice versa."""
+    names = sorted(tensors)
+    data = bytearray()
+    entries = []
+    # key "" -> BundleHeaderProto{num_shards = 1, endianness = LITTLE (0, default), version{producer = 1}}
+    header = _field(1, 0, _enc_varint(1)) + _field(3, 2, _field(1, 0, _enc_varint(1)))
+    entries.append((b"", header))
+    for name in names:
+        arr = np.asarray(tensors[name])          # (ascontiguousarray would turn a 0-d variable into shape (1,))
+        dt = arr.dtype.newbyteorder("<") if arr.dtype.byteorder == ">" else arr.dtype
+        if np.dtype(dt) not in _DTYPE_ENUM:
+            raise ValueError("%s: dtype %s cannot be stored" % (name, arr.dtype))
+        raw = arr.astype(dt, copy=False).tobytes()
+        shape = b"".join(_field(2, 2, _field(1, 0, _enc_varint(int(d)))) for d in arr.shape)
+        entry = _field(1, 0, _enc_varint(_DTYPE_ENUM[np.dtype(dt)])) + _field(2, 2, shape)
+        if len(data):
+            entry += _field(4, 0, _enc_varint(len(data)))
+        entry += _field(5, 0, _enc_varint(len(raw))) + _field(6, 5, struct.pack("<I", masked_crc32c(raw)))
+        entries.append((name.encode(), entry))
+        data += raw
+    with open(prefix + ".data-00000-of-00001", "wb") as f:
+        f.write(bytes(data))
+
+    def with_trailer(block: bytes) -> bytes:
+        return block + b"\x00" + struct.pack("<I", masked_crc32c(block + b"\x00"))
+    out = bytearray()
+    data_block = _block(entries)
+    data_handle = _enc_varint(0) + _enc_varint(len(data_block))
+    out += with_trailer(data_block)
+    meta_off = len(out)
+    meta_block = _block([])
+    out += with_trailer(meta_block)
+    index_off = len(out)
+    index_block = _block([(names[-1].encode() if names else b"", data_handle)])
+    out += with_trailer(index_block)
+    footer = _enc_varint(meta_off) + _enc_varint(len(meta_block)) + _enc_varint(index_off) + _enc_varint(len(index_block))
+    footer += b"\x00" * (40 - len(footer)) + struct.pack("<Q", _MAGIC)
+    out += footer
+    with open(prefix + ".index", "wb") as f:
+        f.write(bytes(out))
+
+
+def verify_bundle_crcs(prefix: str) -> int:
+    """Re-computes the per-tensor crc32c of a bundle against the stored values; returns the number of tensors checked
+    (raises on a mismatch).  Used on the reference's shipped checkpoints to pin this file's CRC / format code."""
+    r = BundleReader(prefix)
+    with open(prefix + ".index", "rb") as f:
+        idx = f.read()
+    footer = idx[-48:]
+    pos = 0
+    _, pos = _varint(footer, pos); _, pos = _varint(footer, pos)
+    index_off, pos = _varint(footer, pos)
+    index_size, pos = _varint(footer, pos)
+    with open(prefix + ".data-00000-of-00001", "rb") as f:
+        blob = f.read()
+    n = 0
+    for _, handle in _block_entries(idx, index_off, index_size):
+        boff, p = _varint(handle, 0)
+        bsize, p = _varint(handle, p)
+        stored_block_crc = struct.unpack_from("<I", idx, boff + bsize + 1)[0]
+        if masked_crc32c(idx[boff:boff + bsize + 1]) != stored_block_crc:
+            raise ValueError("index block crc mismatch in %s" % prefix)
+        for key, value in _block_entries(idx, boff, bsize):
+            if key == b"":
+                continue
+            e = _parse_proto(value)
+            offset = int(e.get(4, [0])[0]); size = int(e[5][0])
+            stored = struct.unpack("<I", e[6][0])[0]
+            if masked_crc32c(blob[offset:offset + size]) != stored:
+                raise ValueError("crc mismatch for %s in %s" % (key.decode(), prefix))
+            n += 1
+    assert n == len(r.entries)
+    return n

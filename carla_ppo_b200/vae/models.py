@@ -66,6 +66,21 @@ def _loss_type(loss_fn) -> int:
     return lt
 
 
+# ----------------------------------------------------------------------------- data-parallel host logic
+def dp_noise_rows(torch, generator, batch, z_dim, rank, world, device):
+    """This rank's rows of the noise the GLOBAL batch draws: all ranks hold the same generator state, draw
+    [world*batch, z] and keep rows [rank*batch, (rank+1)*batch) -- together exactly the single-process draw."""
+    full = torch.randn(batch * world, z_dim, generator=generator, device=device, dtype=torch.float32)
+    return full[rank * batch:(rank + 1) * batch].contiguous()
+
+
+def dp_shared_permutation(torch, dist, indices, device):
+    """Every rank adopts rank 0's epoch permutation (ranks seed np.random independently)."""
+    perm = torch.from_numpy(np.ascontiguousarray(indices, dtype=np.int64)).to(device)
+    dist.broadcast(perm, 0)
+    return perm.cpu().numpy()
+
+
 class _Placeholder:
     """Stands in for the TF tensors callers only inspect (``vae.sample.shape[1]``, inspect_vae.py:100)."""
 
@@ -80,7 +95,7 @@ class VAE:
     def __init__(self, source_shape, target_shape, build_encoder_fn=None, build_decoder_fn=None,
                  z_dim=512, beta=1.0, learning_rate=1e-4, lr_decay=0.98, kl_tolerance=0.0,
                  model_dir=".", loss_fn=bce_loss, training=True, reuse=None, seed=None,
-                 data_parallel=False, device=None, **kwargs):
+                 data_parallel=False, device=None, resident_dataset=True, **kwargs):
         # unknown kwargs (e.g. models_dir="vae", vae_common.py:21) are swallowed like the reference does
         self.source_shape = tuple(int(v) for v in source_shape)
         self.target_shape = tuple(int(v) for v in (source_shape if target_shape is None else target_shape))
@@ -98,6 +113,7 @@ class VAE:
         self.loss_fn = loss_fn
         self.loss_type = _loss_type(loss_fn)
         self.data_parallel = bool(data_parallel)
+        self._resident_dataset = bool(resident_dataset)
         self._seed = seed
         self._device = device
 
@@ -130,6 +146,9 @@ class VAE:
         self._torch, self._libh = torch, lib
         if self._device is None:
             self._device = torch.device("cuda", torch.cuda.current_device())
+        self._device = torch.device(self._device)
+        if self._device.index is None:
+            self._device = torch.device("cuda", torch.cuda.current_device())
         dev = self._device
         n = lib.cpb_vae_num_tensors()
         offs = (C.c_int64 * n)(); sizes = (C.c_int64 * n)(); shapes = (C.c_int32 * (4 * n))()
@@ -154,7 +173,7 @@ class VAE:
         self._flags = torch.zeros(1, dtype=torch.int32, device=dev)
         self._noise_gen = torch.Generator(device=dev)
         self._noise_gen.manual_seed(0 if self._seed is None else int(self._seed))
-        self.set_weights(self._initial_weights())
+        self.set_weights(self._initial_weights())      # (+ broadcast from rank 0 when data_parallel)
         self.sess = self            # truthy stand-in; some callers test `vae.sess`
         self.step_idx = 0
         if init_logging:
@@ -190,6 +209,30 @@ class VAE:
         if self.sess is None:
             raise CpbError("init_session() has not been called")
 
+    def _on_device(self):
+        """Context manager making this model's device current: the C library launches on the CURRENT CUDA device and the
+        buffers live on self._device (a model built with device=cuda:1 must work while cuda:0 is current)."""
+        return self._torch.cuda.device(self._device)
+
+    def _stream(self):
+        return _lib.current_stream_handle(self._device)
+
+    def _call(self, name, *args):
+        with self._on_device():
+            return _lib.check(getattr(self._libh, name)(*args), name)
+
+    def _broadcast_state(self):
+        """data_parallel: every rank adopts rank 0's parameters and optimiser state (different seeds, or a checkpoint only
+        rank 0 has, would otherwise train divergent replicas with summed gradients and no error)."""
+        world, dist = self._world()
+        if world == 1:
+            return
+        bufs = [self.params]
+        if self.training:
+            bufs += [self.adam_m, self.adam_v, self.adam_powers]
+        for b in bufs:
+            dist.broadcast(b, 0)
+
     # ------------------------------------------------------------------ weights in / out
     def set_weights(self, weights: Dict[str, np.ndarray], adam_m=None, adam_v=None, powers=None):
         """weights: {TF variable name without the ``vae/`` scope: array in the TF layout}."""
@@ -213,6 +256,8 @@ class VAE:
                 buf.copy_(torch.from_numpy(h))
             p = (ADAM_BETA1, ADAM_BETA2) if powers is None else powers
             self.adam_powers.copy_(torch.tensor([float(p[0]), float(p[1])], dtype=torch.float32))
+        if self.data_parallel:
+            self._broadcast_state()
 
     def _unflatten(self, flat_tensor) -> Dict[str, np.ndarray]:
         host = flat_tensor.detach().cpu().numpy()
@@ -231,9 +276,11 @@ class VAE:
         return self._unflatten(self.grads)
 
     # ------------------------------------------------------------------ checkpoints
-    def save(self):
-        """Own format (one .npz per checkpoint + the text ``checkpoint`` state file tf.train.Saver keeps,
-        max_to_keep=5) under the reference's directory layout (vae/models.py:172-175)."""
+    def save(self, tf_format=False):
+        """One .npz per checkpoint + the text ``checkpoint`` state file tf.train.Saver keeps (max_to_keep=5) under
+        the reference's directory layout (vae/models.py:172-175).  ``tf_format=True`` writes the SAME variables as a
+        TF-V2 tensor bundle (``model.ckpt-N.index`` / ``.data-00000-of-00001``, tf_bundle.write_bundle) instead, which
+        the reference's own ``saver.restore`` reads."""
         self._require_session()
         step = int(self.step_idx)
         prefix = os.path.join(self.checkpoint_dir, "model.ckpt-%d" % step)
@@ -246,7 +293,11 @@ class VAE:
             pw = self.adam_powers.cpu().numpy()
             blob["vae/beta1_power"], blob["vae/beta2_power"] = pw[0], pw[1]
         blob["vae/step_idx"] = np.int32(step)
-        np.savez(prefix + ".npz", **blob)
+        if tf_format:
+            from ..tf_bundle import write_bundle
+            write_bundle(prefix, {k: np.asarray(v) for k, v in blob.items()})
+        else:
+            np.savez(prefix + ".npz", **blob)
         state = os.path.join(self.checkpoint_dir, "checkpoint")
         kept = []
         if os.path.isfile(state):
@@ -255,7 +306,7 @@ class VAE:
         name = os.path.basename(prefix)
         kept = [k for k in kept if k != name] + [name]
         for old in kept[:-5]:
-            for ext in (".npz",):
+            for ext in (".npz", ".index", ".data-00000-of-00001"):
                 try:
                     os.remove(os.path.join(self.checkpoint_dir, old + ext))
                 except OSError:
@@ -350,7 +401,14 @@ class VAE:
             raise ValueError("verify_range: target_states outside [0, 1] (reference vae/models.py:24-30, 90)")
 
     def _eps(self, batch):
-        return self._torch.randn(batch, self.z_dim, generator=self._noise_gen, device=self._device, dtype=self._torch.float32)
+        """Standard-normal draws for `batch` rows of THIS rank.  data_parallel: every rank holds the same generator state
+        (same seed), draws the noise of the whole global batch and keeps its own contiguous rows -- so the global batch
+        sees world*batch independent rows, exactly the rows the single-GPU step would draw for the same seed."""
+        torch = self._torch
+        world, dist = self._world()
+        if world == 1:
+            return torch.randn(batch, self.z_dim, generator=self._noise_gen, device=self._device, dtype=torch.float32)
+        return dp_noise_rows(torch, self._noise_gen, batch, self.z_dim, dist.get_rank(), world, self._device)
 
     # ------------------------------------------------------------------ inference surface
     def encode(self, source_states):
@@ -366,9 +424,9 @@ class VAE:
         logvar = torch.empty_like(mean) if return_logvar else None
         ws = self._workspace(b, _lib.WS_ENCODE)
         cfg = self._config(b, self._frame_dtype(x))
-        _lib.check(self._libh.cpb_vae_encode(C.byref(cfg), _lib.ptr(self.params), _lib.ptr(x), _lib.ptr(mean),
+        self._call("cpb_vae_encode", C.byref(cfg), _lib.ptr(self.params), _lib.ptr(x), _lib.ptr(mean),
                                              _lib.ptr(logvar), _lib.ptr(self._flags), _lib.ptr(ws), ws.numel(),
-                                             _lib.current_stream_handle()), "cpb_vae_encode")
+                                             self._stream())
         if check:
             self._check_flags()
         return (mean, logvar) if return_logvar else mean
@@ -383,8 +441,8 @@ class VAE:
         out = torch.empty(b, 80 * 160 * self.target_shape[2], dtype=torch.float32, device=self._device)
         ws = self._workspace(b, _lib.WS_FORWARD)
         cfg = self._config(b)
-        _lib.check(self._libh.cpb_vae_decode(C.byref(cfg), _lib.ptr(self.params), _lib.ptr(zt), _lib.ptr(out),
-                                             _lib.ptr(ws), ws.numel(), _lib.current_stream_handle()), "cpb_vae_decode")
+        self._call("cpb_vae_decode", C.byref(cfg), _lib.ptr(self.params), _lib.ptr(zt), _lib.ptr(out),
+                                             _lib.ptr(ws), ws.numel(), self._stream())
         return out.cpu().numpy()
 
     decode = generate_from_latent
@@ -417,10 +475,10 @@ class VAE:
             rec = torch.empty(b, 80 * 160 * self.target_shape[2], dtype=torch.float32, device=self._device)
         ws = self._workspace(b, _lib.WS_FORWARD)
         cfg = self._config(b, self._frame_dtype(x), self._frame_dtype(y), loss_scale)
-        _lib.check(self._libh.cpb_vae_forward(C.byref(cfg), _lib.ptr(self.params), _lib.ptr(x), _lib.ptr(y),
+        self._call("cpb_vae_forward", C.byref(cfg), _lib.ptr(self.params), _lib.ptr(x), _lib.ptr(y),
                                               _lib.ptr(eps), _lib.ptr(losses), _lib.ptr(mean), _lib.ptr(logvar),
                                               _lib.ptr(z), _lib.ptr(rec), _lib.ptr(self._flags), _lib.ptr(ws),
-                                              ws.numel(), _lib.current_stream_handle()), "cpb_vae_forward")
+                                              ws.numel(), self._stream())
         return dict(losses=losses, mean=mean, logvar=logvar, z=z, reconstruction=rec)
 
     def get_step_idx(self):
@@ -445,16 +503,17 @@ class VAE:
         b = x.shape[0]
         ws = self._workspace(b, _lib.WS_TRAIN)
         cfg = self._config(b, self._frame_dtype(x), self._frame_dtype(y), loss_scale)
-        _lib.check(self._libh.cpb_vae_loss_grad(C.byref(cfg), _lib.ptr(self.params), _lib.ptr(x), _lib.ptr(y),
+        self._call("cpb_vae_loss_grad", C.byref(cfg), _lib.ptr(self.params), _lib.ptr(x), _lib.ptr(y),
                                                 _lib.ptr(eps), _lib.ptr(self.grads), _lib.ptr(self._losses),
                                                 _lib.ptr(self._flags), _lib.ptr(ws), ws.numel(),
-                                                _lib.current_stream_handle()), "cpb_vae_loss_grad")
+                                                self._stream())
 
-    def adam_device(self):
-        _lib.check(self._libh.cpb_adam_apply(_lib.ptr(self.params), _lib.ptr(self.grads), _lib.ptr(self.adam_m),
-                                             _lib.ptr(self.adam_v), self._total, _lib.ptr(self.adam_powers),
-                                             self.base_learning_rate, None, ADAM_BETA1, ADAM_BETA2, ADAM_EPS,
-                                             _lib.current_stream_handle()), "cpb_adam_apply")
+    def adam_device(self, guard=None):
+        """TF ApplyAdam on the flat buffers.  ``guard``: device word (tensor) that vetoes the update when non-zero --
+        the verify_range flag, so that an out-of-range batch leaves the model untouched like the reference's tf.Assert."""
+        self._call("cpb_adam_apply_guarded", _lib.ptr(self.params), _lib.ptr(self.grads), _lib.ptr(self.adam_m),
+                   _lib.ptr(self.adam_v), self._total, _lib.ptr(self.adam_powers), self.base_learning_rate, None,
+                   ADAM_BETA1, ADAM_BETA2, ADAM_EPS, _lib.ptr(guard), self._stream())
 
     def train_step_device(self, x, y, eps=None):
         """One minibatch step on device tensors (this rank's shard when data_parallel).  Returns the device
@@ -465,9 +524,14 @@ class VAE:
             eps = self._eps(x.shape[0])
         world, dist = self._world()
         self.loss_grad_device(x, y, eps, 1.0 / world)
+        guard = self._flags
         if world > 1:
-            dist.all_reduce(self._gradbuf)        # ONE NCCL all-reduce: flat gradient + the two loss scalars
-        self.adam_device()
+            # ONE NCCL all-reduce: flat gradient + the two loss scalars + the verify_range flag (as a float: the sum is
+            # non-zero on every rank when ANY rank saw an out-of-range value, so all replicas skip the update together)
+            guard = self._gradbuf[self._total + 2:self._total + 3]
+            guard.copy_(self._flags)
+            dist.all_reduce(self._gradbuf)
+        self.adam_device(guard)
         return self._losses
 
     def train_step(self, source, target, eps=None):
@@ -503,11 +567,11 @@ class VAE:
         ws = self._workspace(b, _lib.WS_TRAIN)
         losses = np.zeros(2, np.float32)
         flags = np.zeros(1, np.int32)
-        _lib.check(self._libh.cpb_vae_train_step_host(
+        self._call("cpb_vae_train_step_host", 
             C.byref(cfg), _lib.ptr(self.params), _lib.ptr(self.grads), _lib.ptr(self.adam_m), _lib.ptr(self.adam_v),
             _lib.ptr(self.adam_powers), self.base_learning_rate, _lib.ptr(src), _lib.ptr(src if same else tgt),
             _lib.ptr(eps), _lib.ptr(losses), _lib.ptr(flags), _lib.ptr(st), st.numel(), _lib.ptr(ws), ws.numel(),
-            _lib.current_stream_handle()), "cpb_vae_train_step_host")
+            self._stream())
         if flags[0] & 1:
             raise ValueError("verify_range: source_states outside [0, 1]")
         if flags[0] & 2:
@@ -604,12 +668,19 @@ class VAE:
             return self._to_device_frames(arr, channels)
         a = np.asarray(arr)
         key = (id(arr), a.__array_interface__["data"][0], a.shape, str(a.dtype))
+        # content fingerprint: ~64 K values sampled at a fixed stride over the whole array.  The reference re-feeds host
+        # data every step; a caller that rewrites the array in place between epochs (augmentation, buffer reuse) must not
+        # silently train on the stale GPU copy.  (Edits that miss every sampled value are not detected: call
+        # clear_dataset_cache(), or pass resident_dataset=False to the constructor to upload on every epoch.)
+        flat = a.reshape(-1)
+        probe = flat[::max(1, flat.size // 65536)]
+        finger = (float(probe.astype(np.float64).sum()), float(probe[::7].astype(np.float64).sum()))
         hit = self._dataset_cache.get(key)
-        if hit is None:
+        if hit is None or hit[1] != finger or not self._resident_dataset:
             if len(self._dataset_cache) >= 4:
                 self._dataset_cache.clear()
-            hit = self._dataset_cache[key] = self._to_device_frames(a, channels)
-        return hit
+            hit = self._dataset_cache[key] = (self._to_device_frames(a, channels), finger)
+        return hit[0]
 
     def clear_dataset_cache(self):
         self._dataset_cache.clear()
@@ -622,6 +693,8 @@ class VAE:
         ys = xs if target is source else self._device_dataset(target, self.target_shape[2])
         indices = np.arange(n)
         np.random.shuffle(indices)                      # same host RNG call as the reference (:208-209)
+        if world > 1:                                   # one shuffle for the whole job: rank 0's (ranks seed np.random independently)
+            indices = dp_shared_permutation(torch, dist, indices, self._device)
         steps = n // batch_size                         # tail N % B dropped like the reference (:211)
         rank = dist.get_rank() if world > 1 else 0
         shard = batch_size // world

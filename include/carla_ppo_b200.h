@@ -116,8 +116,17 @@ int32_t cpb_adam_apply(float* params, const float* grads, float* m, float* v, in
                        float* powers, float lr, const float* lr_dev, float beta1, float beta2,
                        float epsilon, void* stream);
 
+/* The same with a guard: `guard` (nullable) points at one 32-bit device word; when any of its bits is set the whole
+ * update (parameters, m, v, beta powers) is skipped.  Used with the verify_range flag word: the reference's tf.Assert
+ * (vae/models.py:24-30) aborts the sess.run before ApplyAdam, so an out-of-range batch must not touch the model.
+ * A data-parallel caller passes the all-reduced flag (any 32-bit pattern, e.g. a float sum; only == 0 matters). */
+int32_t cpb_adam_apply_guarded(float* params, const float* grads, float* m, float* v, int64_t n,
+                               float* powers, float lr, const float* lr_dev, float beta1, float beta2,
+                               float epsilon, const void* guard, void* stream);
+
 /* One reference minibatch step: sess.run([train_step, ...]) of VAE.train_one_epoch
- * (vae/models.py:213-216) = cpb_vae_loss_grad + cpb_adam_apply on one GPU. */
+ * (vae/models.py:213-216) = cpb_vae_loss_grad + cpb_adam_apply_guarded(guard = flags) on one GPU: when `flags` is given
+ * and a source/target value is outside [0,1], the losses are still written but the model is left untouched. */
 int32_t cpb_vae_train_step(const cpb_vae_config* cfg, float* params, float* grads, float* adam_m,
                            float* adam_v, float* adam_powers, float lr, const void* source,
                            const void* target, const float* eps, float* losses, int32_t* flags,
@@ -188,7 +197,8 @@ int32_t cpb_gae(const double* rewards, const double* values, double bootstrap_va
 
 /* The driver's whole update block (train.py:171-207) with no host round trip:
  * GAE -> returns -> normalised advantages -> theta_old <- theta -> num_epochs x ceil(T/batch)
- * minibatch Adam steps following perms[num_epochs][T] (int32 index order of each epoch).
+ * minibatch Adam steps following perms[num_epochs][T] (int32 index order of each epoch; may be NULL when
+ * num_epochs == 0).
  * metrics: float[num_epochs*ceil(T/batch)][5] (optional). */
 int32_t cpb_ppo_learn(const cpb_ppo_config* cfg, float* params, float* params_old, float* grads,
                       float* adam_m, float* adam_v, float* adam_powers, const float* lr_dev,
@@ -204,7 +214,7 @@ int32_t cpb_ppo_learn(const cpb_ppo_config* cfg, float* params, float* params_ol
  *               not cover (3-channel edge layers, dense heads, weight gradients). */
 int32_t cpb_set_math_mode(int32_t mode);
 /* Debug / test hooks (not part of the reference-facing surface): workspace buffer offsets in bytes for
- * [xp,a1,a2,a3,a4,heads,z,d1,b1,b2,b3,logits_p,gA,gB] (-1 = absent in that mode), and a dense
+ * [xp,a1,a2,a3,a4,heads,z,d1,b1,b2,b3,logits_p,gA,gB,frame_loss,kl_rows] (-1 = absent in that mode), and a dense
  * D[M,N] = A[M,K] * Bt[N,K]^T through the tensor-core kernel (scratch: 2*N*K + M*K floats). */
 int32_t cpb_debug_vae_buffer_offsets(int32_t batch, int32_t target_channels, int32_t z_dim, int32_t mode,
                                      int64_t* offsets, int32_t capacity);

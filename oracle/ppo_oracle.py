@@ -143,6 +143,10 @@ def loss_and_grads(params, params_old, s, a, ret, adv, low, high, epsilon=0.2, v
     s = np.asarray(s, dtype); a = np.asarray(a, dtype); ret = np.asarray(ret, dtype); adv = np.asarray(adv, dtype)
     low = np.asarray(low, dtype); high = np.asarray(high, dtype)
     bsz = s.shape[0]
+    # the graph's Const nodes are float32 (shipped .meta: clip_by_value/y = 0.800000011920929, clip_by_value/Minimum/y =
+    # 1.2000000476837158, mul_3/y = 0.009999999776482582; tests/test_oracle.py pins them): use the rounded values
+    clip_lo, clip_hi = float(np.float32(1.0 - epsilon)), float(np.float32(1.0 + epsilon))
+    value_scale, entropy_scale = float(np.float32(value_scale)), float(np.float32(entropy_scale))
     keep = {}
     mu, v = forward(p, s, low, high, keep)
     mu_old, _ = forward(po, s, low, high)
@@ -153,7 +157,7 @@ def loss_and_grads(params, params_old, s, a, ret, adv, low, high, epsilon=0.2, v
     ratio = np.exp(logp - logp_old)                       # [B,1]
     advc = adv[:, None]
     unclipped = ratio * advc
-    clipped = np.clip(ratio, 1.0 - epsilon, 1.0 + epsilon) * advc
+    clipped = np.clip(ratio, clip_lo, clip_hi) * advc
     policy_loss = np.mean(np.minimum(unclipped, clipped))
     value_loss = np.mean((v - ret) ** 2) * value_scale
     entropy_loss = np.sum(ENTROPY_CONST + logstd) * entropy_scale
@@ -168,7 +172,7 @@ def loss_and_grads(params, params_old, s, a, ret, adv, low, high, epsilon=0.2, v
     # otherwise to the clipped branch whose own gradient is zero outside [1-eps, 1+eps]
     # (inside it, clipped == unclipped and the first branch already took it).
     first = unclipped <= clipped
-    inside = (ratio >= 1.0 - epsilon) & (ratio <= 1.0 + epsilon)
+    inside = (ratio >= clip_lo) & (ratio <= clip_hi)
     dratio = np.where(first, advc, np.where(inside, advc, 0.0)) * (-1.0 / bsz)
     dlogp = dratio * ratio                                # [B,1]
     diff = (a - mu) / std                                 # [B,A]

@@ -92,14 +92,16 @@ class TorchAdamTF:
 
     def __init__(self, p, lr, beta1=0.9, beta2=0.999, eps=1e-8):
         self.p = p
-        self.lr, self.b1, self.b2, self.eps = lr, beta1, beta2, eps
+        # float32-rounded graph constants, like vae_oracle.ADAM_* (pinned to the shipped .meta files)
+        f32 = lambda v: float(np.float32(v))
+        self.lr, self.b1, self.b2, self.eps = f32(lr), f32(beta1), f32(beta2), f32(eps)
         self.m = {k: torch.zeros_like(v) for k, v in p.items()}
         self.v = {k: torch.zeros_like(v) for k, v in p.items()}
-        self.b1p, self.b2p = beta1, beta2
+        self.b1p, self.b2p = self.b1, self.b2
 
     @torch.no_grad()
     def step(self, lr=None):
-        lr = self.lr if lr is None else lr
+        lr = self.lr if lr is None else float(np.float32(lr))
         alpha = lr * math.sqrt(1.0 - self.b2p) / (1.0 - self.b1p)
         for k, t in self.p.items():
             if t.grad is None:
@@ -166,6 +168,9 @@ def ppo_logp(mu, logstd, a):
 
 def ppo_loss(p, p_old, s, a, ret, adv, low, high, epsilon=0.2, value_scale=0.5, entropy_scale=0.01):
     """ppo.py:119-134.  Returns loss, (policy_loss, value_loss, entropy_loss, mean_ratio)."""
+    # float32-rounded graph constants (see ppo_oracle.loss_and_grads; pinned to the shipped .meta)
+    clip_lo, clip_hi = float(np.float32(1.0 - epsilon)), float(np.float32(1.0 + epsilon))
+    value_scale, entropy_scale = float(np.float32(value_scale)), float(np.float32(entropy_scale))
     mu, v = ppo_forward(p, s, low, high)
     with torch.no_grad():
         mu_old, _ = ppo_forward(p_old, s, low, high)
@@ -173,7 +178,7 @@ def ppo_loss(p, p_old, s, a, ret, adv, low, high, epsilon=0.2, value_scale=0.5, 
     logp = ppo_logp(mu, p["action_logstd"], a)
     ratio = torch.exp(logp - logp_old)
     advc = adv.unsqueeze(-1)
-    policy_loss = torch.mean(torch.minimum(ratio * advc, torch.clamp(ratio, 1.0 - epsilon, 1.0 + epsilon) * advc))
+    policy_loss = torch.mean(torch.minimum(ratio * advc, torch.clamp(ratio, clip_lo, clip_hi) * advc))
     value_loss = torch.mean((v - ret) ** 2) * value_scale
     entropy = torch.sum(_ENTROPY_CONST + p["action_logstd"]).expand(s.shape[0])
     entropy_loss = torch.mean(entropy) * entropy_scale

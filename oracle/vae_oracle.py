@@ -294,9 +294,13 @@ def loss_and_grads(params, x, y, eps, loss_type="mse", beta=1.0, kl_tolerance=0.
 
 
 # ----------------------------------------------------------------------------- optimiser
-ADAM_BETA1 = 0.9
-ADAM_BETA2 = 0.999
-ADAM_EPS = 1e-8
+# The reference's graph holds these as float32 constants (shipped .meta: vae/Adam/beta1 = 0.8999999761581421,
+# beta2 = 0.9990000128746033, epsilon = 9.99999993922529e-09, learning_rate = 9.999999747378752e-05; pinned by
+# tests/test_oracle.py::test_constants_pinned_to_the_shipped_graphs) and TF's ApplyAdam kernel computes 1 - beta in
+# float32, so the float64 restatement uses the float32-ROUNDED values, not the Python literals.
+ADAM_BETA1 = float(np.float32(0.9))
+ADAM_BETA2 = float(np.float32(0.999))
+ADAM_EPS = float(np.float32(1e-8))
 
 
 def adam_init_state(params, dtype=np.float64):
@@ -311,6 +315,7 @@ def adam_apply(params, grads, state, lr, beta1=ADAM_BETA1, beta2=ADAM_BETA2, eps
         m += (g - m) * (1 - beta1);  v += (g*g - v) * (1 - beta2);  p -= alpha * m / (sqrt(v) + eps)
     then beta{1,2}_power *= beta{1,2} (AdamOptimizer._finish).  The power accumulators start at
     beta1 / beta2 (so the first step uses t = 1)."""
+    lr = float(np.float32(lr))                 # the learning-rate Const of the graph is float32
     alpha = lr * np.sqrt(1.0 - state["beta2_power"]) / (1.0 - state["beta1_power"])
     for k in params:
         g = grads[k]

@@ -9,9 +9,10 @@ import types
 import numpy as np
 import pytest
 
-from helpers import committed_frames, kat, rel_l2, shipped_ppo, shipped_vae_weights
+from helpers import GOLDEN, committed_frames, kat, rel_l2, shipped_ppo, shipped_vae_weights
 
 REF = "/root/reference"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_vae_backward_matches_autograd():
@@ -159,3 +160,97 @@ def test_committed_fixtures_equal_the_shipped_checkpoints():
     for k in pol:
         assert np.array_equal(pol[k], r2.get("policy/" + k))
     assert int(r2.get("episode_counter")) == 705
+
+
+# ----------------------------------------------------------------------------- reference-held graph constants
+def _meta_constants():
+    import json
+    with open(os.path.join(GOLDEN, "meta_constants.json")) as f:
+        return json.load(f)
+
+
+def test_constants_pinned_to_the_shipped_graphs():
+    """the numeric constants of the reference's SHIPPED TF graphs (MetaGraphDefs written by
+    TF 1.13.1, extracted into tests/golden/meta_constants.json by make_meta_constants.py) are the only reference-held
+    pin of the PPO loss: the oracle's and the CUDA kernels' constants must be exactly these float32 values."""
+    from oracle import ppo_oracle as po, vae_oracle as vo
+    mc = _meta_constants()
+    p, v = mc["ppo"]["constants"], mc["vae"]["constants"]
+    assert po.LOG_SQRT_2PI == p["log_prob_const"] and po.ENTROPY_CONST == p["entropy_const"] and p["log_prob_half"] == -0.5
+    # clip bounds: Python 1 -/+ 0.2 rounded to float32 (what the oracle uses) ...
+    assert float(np.float32(1.0 - 0.2)) == p["clip_low"] and float(np.float32(1.0 + 0.2)) == p["clip_high"]
+    # ... and what the CUDA head kernel computes in float32 from eps_clip = 0.2f (ppo.cu: 1.f -/+ a.eps_clip)
+    assert float(np.float32(1) - np.float32(0.2)) == p["clip_low"] and float(np.float32(1) + np.float32(0.2)) == p["clip_high"]
+    assert float(np.float32(0.01)) == p["entropy_scale"] and p["value_scale"] == 1.0
+    assert p["mean_affine_add"] == 1.0 and p["mean_affine_div"] == 2.0        # mu = low + (tanh + 1)/2 * (high - low)
+    for c in (p, v):
+        assert vo.ADAM_BETA1 == c["adam_beta1"] == c["beta1_power_init"]
+        assert vo.ADAM_BETA2 == c["adam_beta2"] == c["beta2_power_init"]
+        assert vo.ADAM_EPS == c["adam_epsilon"]
+        assert float(np.float32(1e-4)) == c["learning_rate"]
+    assert v["kl_minus_half"] == -0.5 and v["kl_one"] == 1.0 and v["reparam_half"] == 0.5
+    assert v["range_low"] == 0.0 and v["range_high"] == 1.0 and v["beta"] == 1.0
+    # the tie rule of tf.minimum's gradient (LessEqual + Select: ties go to the UNclipped branch) -- what
+    # ppo_oracle.loss_and_grads ("first = unclipped <= clipped") and ppo_head_kernel implement
+    assert mc["ppo"]["surrogate"]["min_grad_select"] == ["LessEqual", "Select"]
+    assert mc["ppo"]["surrogate"]["Minimum_inputs"] == ["mul", "mul_1"]
+    # layer semantics the restatement assumes (NHWC, VALID, stride 2, no dilation; transposed conv = Conv2DBackpropInput)
+    for name, op in mc["vae"]["conv_ops"].items():
+        assert op["strides"] == [1, 2, 2, 1] and op["padding"] == "VALID" and op["data_format"] == "NHWC" and op["dilations"] == [1, 1, 1, 1]
+        assert op["op"] == ("Conv2D" if "encoder" in name else "Conv2DBackpropInput")
+    for need in ("Conv2DBackpropFilter", "Conv2DBackpropInput", "Conv2D", "BiasAddGrad", "ReluGrad", "MatMul", "AddN"):
+        assert need in mc["vae"]["gradient_ops"]
+    # variable shapes of both graphs == the oracle's parameter tables (the rgb VAE; and the seg VAE copy inside the agent graph)
+    for name, shape in vo.param_shapes(target_channels=3).items():
+        assert tuple(mc["vae"]["variables"]["vae/" + name]) == shape, name
+    for name, shape in vo.param_shapes(target_channels=1).items():
+        assert tuple(mc["ppo"]["variables"]["vae/" + name]) == shape, name
+    for name, shape in po.param_shapes().items():
+        assert tuple(mc["ppo"]["variables"]["policy/" + name]) == shape == tuple(mc["ppo"]["variables"]["policy_old/" + name])
+
+
+def test_cuda_sources_use_the_pinned_constants():
+    """The kernels spell the same literals (grep-level check; the GPU tests check the numerics)."""
+    mc = _meta_constants()["ppo"]["constants"]
+    src = open(os.path.join(ROOT, "carla_ppo_b200", "csrc", "ppo.cu")).read()
+    assert ("kLogSqrt2Pi = %sf" % repr(mc["log_prob_const"])) in src
+    assert ("kEntropyConst = %sf" % repr(mc["entropy_const"])) in src
+    assert "unclipped <= clipped" in src
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+def test_meta_constants_file_equals_the_shipped_graphs():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_meta_constants", os.path.join(GOLDEN, "make_meta_constants.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.extract() == _meta_constants()
+
+
+# ----------------------------------------------------------------------------- TF-V2 bundle writer
+def test_tf_bundle_writer_round_trip(tmp_path):
+    from carla_ppo_b200 import tf_bundle as tb
+    rs = np.random.RandomState(0)
+    tensors = {"vae/encoder/conv1/kernel": rs.randn(4, 4, 3, 32).astype(np.float32), "vae/step_idx": np.int32(7),
+               "beta1_power": np.float32(0.5), "a/b": np.arange(10, dtype=np.int64), "z": rs.randn(3, 5)}
+    tb.write_bundle(str(tmp_path / "model.ckpt-7"), tensors)
+    got = tb.BundleReader(str(tmp_path / "model.ckpt-7")).all()
+    assert set(got) == set(tensors)
+    for k, v in tensors.items():
+        assert got[k].dtype == np.asarray(v).dtype and got[k].shape == np.asarray(v).shape and np.array_equal(got[k], v), k
+    assert tb.verify_bundle_crcs(str(tmp_path / "model.ckpt-7")) == len(tensors)
+    assert tb.crc32c(b"123456789") == 0xE3069283                      # the CRC-32C check value
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+def test_tf_bundle_crc_and_entries_pinned_to_a_shipped_checkpoint(tmp_path):
+    """The writer's format code against a file TF itself wrote: every stored crc32c of the shipped agent checkpoint
+    verifies with this implementation, and re-writing its tensors reproduces each entry's dtype/shape/size/crc."""
+    from carla_ppo_b200 import tf_bundle as tb
+    prefix = "%s/models/pretrained_agent/checkpoints/model.ckpt-705" % REF
+    assert tb.verify_bundle_crcs(prefix) == 80
+    small = {k: v for k, v in tb.BundleReader(prefix).all().items() if v.size < 40000}
+    tb.write_bundle(str(tmp_path / "x"), small)
+    a, b = tb.BundleReader(prefix), tb.BundleReader(str(tmp_path / "x"))
+    for k in small:
+        assert a.entries[k][:2] == b.entries[k][:2] and a.entries[k][3] == b.entries[k][3]

@@ -144,3 +144,70 @@ def test_checkpoint_round_trip_and_lr_decay(tmp_path):
     assert m2.get_episode_idx() == 1
     w1, w2 = m.get_weights(), m2.get_weights()
     assert all(np.array_equal(w1[k], w2[k]) for k in w1)
+
+
+def _baseline_config3(T=2048, E=4):
+    """SURVEY section 8(d) config 3 / BASELINE configs[2]: T=2048 rollout, 4 epochs x 8 minibatches of 256,
+    shipped agent ckpt-705 (policy, policy_old, warm Adam slots and beta powers), permutations from RandomState(0)."""
+    rs = np.random.RandomState(0)
+    states = rs.randn(T, 67).astype(np.float32)
+    actions = np.clip(rs.randn(T, 2), LOW, HIGH).astype(np.float32)
+    rewards = rs.rand(T)
+    values = rs.randn(T).astype(np.float32)
+    dones = np.zeros(T, bool); dones[-1] = True
+    prs = np.random.RandomState(0)
+    perms = np.stack([prs.permutation(T) for _ in range(E)])
+    return states, actions, rewards, values, dones, perms
+
+
+def test_learn_at_baseline_config3_matches_oracle(tmp_path):
+    """The driver's update block (reference train.py:171-207) at EXACTLY BASELINE configs[2]: parameters, theta_old and
+    the 32 per-minibatch losses vs the float64 restatement; gate = max(1e-5, 2 x the error of the float32 CPU
+    restatement run through the same 32 Adam steps)."""
+    from oracle import ppo_oracle as po
+    pol, z = shipped_ppo("policy")
+    old, _ = shipped_ppo("policy_old")
+    adam_m = {k: z["adam_m/" + k] for k in pol}
+    adam_v = {k: z["adam_v/" + k] for k in pol}
+    powers = (float(z["beta1_power"]), float(z["beta2_power"]))
+    m = make_ppo(tmp_path, pol, old)
+    m.set_weights(pol, old, adam_m, adam_v, powers)
+    T, E, B = 2048, 4, 256
+    s, a, r, v, d, perms = _baseline_config3(T, E)
+    metrics = m.learn(s, a, v, r, d, 0.3, gamma=0.99, lam=0.95, num_epochs=E, batch_size=B, perms=perms, return_metrics=True)
+
+    def restate(dtype):
+        p = {k: x.astype(dtype) for k, x in pol.items()}
+        st = dict(m={k: adam_m[k].astype(dtype) for k in pol}, v={k: adam_v[k].astype(dtype) for k in pol},
+                  beta1_power=powers[0], beta2_power=powers[1])
+        rec = po.learn(p, st, s, a, v, r, d, 0.3, LOW, HIGH, 0.99, 0.95, 1e-4, 0.2, 1.0, 0.01, E, B, perms, dtype=dtype)
+        return p, np.asarray(rec, np.float64)
+    p64, rec64 = restate(np.float64)
+    p32, rec32 = restate(np.float32)
+    got = m.get_weights()
+    for name in p64:
+        gate = max(TOL, 2 * rel_l2(p32[name], p64[name]))
+        assert rel_l2(got[name], p64[name]) < gate, "%s: %.3e (gate %.3e)" % (name, rel_l2(got[name], p64[name]), gate)
+    assert metrics.shape == rec64.shape == (E * (T // B), 5)
+    for col in range(5):
+        gate = max(TOL, 2 * rel_l2(rec32[:, col], rec64[:, col]))
+        assert rel_l2(metrics[:, col], rec64[:, col]) < gate, (col, rel_l2(metrics[:, col], rec64[:, col]), gate)
+    gold = m.get_old_weights()
+    assert all(np.array_equal(gold[k], pol[k]) for k in pol)               # update_old_policy() ran at entry
+    assert m.get_train_step_idx() == 32
+
+
+def test_update_old_policy_and_zero_epoch_learn(tmp_path):
+    """PPO.update_old_policy (ppo.py:275-276) called directly; learn(num_epochs=0) still does theta_old <- theta."""
+    pol, _ = shipped_ppo("policy")
+    old, _ = shipped_ppo("policy_old")
+    m = make_ppo(tmp_path, pol, old)
+    assert not all(np.array_equal(m.get_old_weights()[k], pol[k]) for k in pol)
+    m.update_old_policy()
+    assert all(np.array_equal(m.get_old_weights()[k], pol[k]) for k in pol)
+    m.set_weights(pol, old)
+    s, a, r, v, d = rollout(40, 3)
+    out = m.learn(s, a, v, r, d, 0.1, num_epochs=0, batch_size=16, return_metrics=True)
+    assert out.shape == (0, 5)
+    assert all(np.array_equal(m.get_old_weights()[k], pol[k]) for k in pol)
+    assert all(np.array_equal(m.get_weights()[k], pol[k]) for k in pol)
