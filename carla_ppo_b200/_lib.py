@@ -63,6 +63,7 @@ PROTOTYPES = {
     "cpb_ppo_forward": (_i32, [_PC, _P, _P, _i32, _P, _P, _P, _P, _i64, _P]),
     "cpb_ppo_loss_grad": (_i32, [_PC, _P, _P, _P, _P, _P, _P, _P, _i32, _P, _P, _P, _i64, _P]),
     "cpb_ppo_train_step": (_i32, [_PC, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _i32, _P, _P, _i64, _P]),
+    "cpb_encode_predict": (_i32, [_VC, _P, _P, _P, _i32, _PC, _P, _P, _P, _P, _P, _P, _P, _P, _i64, _P, _i64, _P]),
     "cpb_gae": (_i32, [_P, _P, _f64, _P, _i32, _f64, _f64, _P, _P, _P, _P]),
     "cpb_ppo_learn": (_i32, [_PC, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _f64, _P, _i32, _f64, _f64,
                              _i32, _i32, _P, _P, _P, _i64, _P]),

@@ -3,6 +3,8 @@
 // driver's update block (train.py:171-207).  Everything here is latency-bound (369 505 parameters,
 // minibatches of a few hundred rows): the kernels are small bounds-checked fp32 tile GEMMs, batched
 // over the two trunks (policy / value) so one minibatch step is ~11 launches with no host sync.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "elementwise.cuh"
 
@@ -58,7 +60,7 @@ struct Operand {
 // value load waited on a predicated index load that reused the same register).
 template <int GATHER>
 __device__ __forceinline__ long long a_offset(const Operand& a, int o, int r) {
-    if (GATHER == 1) return (long long)__ldg(a.gather + o) * a.so + (long long)r * a.sr;
+    if (GATHER == 1) return (long long)__ldg(a.gather + o) * a.so + (long long)r * a.sr;      // the index vectors are launch inputs
     if (GATHER == 2) return (long long)o * a.so + (long long)__ldg(a.gather + r) * a.sr;
     return (long long)o * a.so + (long long)r * a.sr;
 }
@@ -78,16 +80,12 @@ struct GemmBatch {
     GemmJob job[6];       // independent GEMMs of one launch (blockIdx.z); all with the same gather mode
 };
 
-template <int GATHER>
-__global__ void __launch_bounds__(64)
-small_gemm_kernel(const __grid_constant__ GemmBatch batch) {
-    const GemmJob& J = batch.job[blockIdx.z];
-    const int m0 = blockIdx.x * TS, n0 = blockIdx.y * TS;
-    if (m0 >= J.M || n0 >= J.N) return;
-    // double-buffered tiles: the global loads of chunk i+1 are in flight (in registers) while chunk i is multiplied
-    __shared__ __align__(16) float As[2][TK][TS + 4];
-    __shared__ __align__(16) float Bs[2][TK][TS + 4];
-    const int tid = threadIdx.x;
+// One 32x32 output tile of job J by a GROUP of 64 threads (tid = 0..63).  `sync()` is the group's barrier: __syncthreads in
+// the stand-alone kernel (one group per CTA), a named barrier in the persistent learn() kernel (four groups per CTA).
+// As / Bs: the group's double-buffered operand tiles [2][TK][TS + 4].
+template <int GATHER, typename Sync>
+__device__ __forceinline__ void gemm_tile(const GemmJob& J, int m0, int n0, bool first_m_tile, int tid,
+                                          float (*As)[TK][TS + 4], float (*Bs)[TK][TS + 4], Sync sync) {
     const int tx = tid & 7, ty = tid >> 3;      // 8 x 8 threads, 4x4 outputs each
     float acc[4][4];
 #pragma unroll
@@ -95,7 +93,7 @@ small_gemm_kernel(const __grid_constant__ GemmBatch batch) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     float csum = 0.f;                            // column-sum lane (threads 0..31 own column n0+tid)
-    const bool do_colsum = J.colsum != nullptr && blockIdx.x == 0;
+    const bool do_colsum = J.colsum != nullptr && first_m_tile;
     const bool a_ofast = J.a.so <= J.a.sr, b_ofast = J.b.so <= J.b.sr;
 
     constexpr int EPT = TS * TK / 64;           // elements per thread per operand and chunk
@@ -107,9 +105,9 @@ small_gemm_kernel(const __grid_constant__ GemmBatch batch) {
             const int f = tid + e * 64;
             int o, r;
             if (a_ofast) { o = f & 31; r = f >> 5; } else { r = f & (TK - 1); o = f / TK; }
-            ra[e] = (m0 + o < J.M && r0 + r < J.R) ? __ldg(J.a.p + a_offset<GATHER>(J.a, m0 + o, r0 + r)) : 0.f;
+            ra[e] = (m0 + o < J.M && r0 + r < J.R) ? __ldcg(J.a.p + a_offset<GATHER>(J.a, m0 + o, r0 + r)) : 0.f;
             if (b_ofast) { o = f & 31; r = f >> 5; } else { r = f & (TK - 1); o = f / TK; }
-            rb[e] = (n0 + o < J.N && r0 + r < J.R) ? __ldg(J.b.p + (long long)(n0 + o) * J.b.so + (long long)(r0 + r) * J.b.sr) : 0.f;
+            rb[e] = (n0 + o < J.N && r0 + r < J.R) ? __ldcg(J.b.p + (long long)(n0 + o) * J.b.so + (long long)(r0 + r) * J.b.sr) : 0.f;
         }
     };
     fetch_chunk(0);
@@ -124,7 +122,7 @@ small_gemm_kernel(const __grid_constant__ GemmBatch batch) {
             if (b_ofast) { o = f & 31; r = f >> 5; } else { r = f & (TK - 1); o = f / TK; }
             Bs[buf][r][o] = rb[e];
         }
-        __syncthreads();
+        sync();
         if (r0 + TK < J.R) fetch_chunk(r0 + TK);
 #pragma unroll
         for (int k = 0; k < TK; ++k) {
@@ -150,13 +148,26 @@ small_gemm_kernel(const __grid_constant__ GemmBatch batch) {
         for (int j = 0; j < 4; ++j) {
             const int n = n0 + tx * 4 + j;
             if (n >= J.N) continue;
-            float v = acc[i][j] + (J.bias ? J.bias[n] : 0.f);
+            float v = acc[i][j] + (J.bias ? __ldcg(J.bias + n) : 0.f);
             if (J.relu) v = fmaxf(v, 0.f);
-            if (J.mask) v = J.mask[(long long)m * J.ldc + n] > 0.f ? v : 0.f;
+            if (J.mask) v = __ldcg(J.mask + (long long)m * J.ldc + n) > 0.f ? v : 0.f;
             J.c[(long long)m * J.ldc + n] = v;
         }
     }
     if (do_colsum && tid < 32 && n0 + tid < J.N) J.colsum[n0 + tid] = csum;
+    sync();          // the next tile of this group reuses As / Bs
+}
+
+template <int GATHER>
+__global__ void __launch_bounds__(64)
+small_gemm_kernel(const __grid_constant__ GemmBatch batch) {
+    const GemmJob& J = batch.job[blockIdx.z];
+    const int m0 = blockIdx.x * TS, n0 = blockIdx.y * TS;
+    if (m0 >= J.M || n0 >= J.N) return;
+    // double-buffered tiles: the global loads of chunk i+1 are in flight (in registers) while chunk i is multiplied
+    __shared__ __align__(16) float As[2][TK][TS + 4];
+    __shared__ __align__(16) float Bs[2][TK][TS + 4];
+    gemm_tile<GATHER>(J, m0, n0, blockIdx.x == 0, threadIdx.x, As, Bs, [] { __syncthreads(); });
 }
 
 int32_t launch_small_gemm(const GemmBatch& b, int njobs, cudaStream_t s) {
@@ -176,7 +187,7 @@ int32_t launch_small_gemm(const GemmBatch& b, int njobs, cudaStream_t s) {
 }
 
 // Y[B,N] = act(X[B,K] W[K,N] + b)
-GemmJob fwd_job(const float* x, const int32_t* idx, int B, int K, const float* w, int N, const float* bias,
+__host__ __device__ GemmJob fwd_job(const float* x, const int32_t* idx, int B, int K, const float* w, int N, const float* bias,
                 float* y, int relu) {
     GemmJob j;
     memset(&j, 0, sizeof(j));
@@ -186,7 +197,7 @@ GemmJob fwd_job(const float* x, const int32_t* idx, int B, int K, const float* w
     return j;
 }
 // dX[B,K] = (dY[B,N] W[K,N]^T) * (H > 0)
-GemmJob bwd_data_job(const float* dy, int B, int N, const float* w, int K, const float* h, float* dx) {
+__host__ __device__ GemmJob bwd_data_job(const float* dy, int B, int N, const float* w, int K, const float* h, float* dx) {
     GemmJob j;
     memset(&j, 0, sizeof(j));
     j.a = Operand{dy, N, 1, nullptr, 0};
@@ -195,7 +206,7 @@ GemmJob bwd_data_job(const float* dy, int B, int N, const float* w, int K, const
     return j;
 }
 // gW[K,N] = X[B,K]^T dY[B,N];  gb[N] = colsum(dY)
-GemmJob bwd_weight_job(const float* x, const int32_t* idx, int B, int K, const float* dy, int N, float* gw, float* gb) {
+__host__ __device__ GemmJob bwd_weight_job(const float* x, const int32_t* idx, int B, int K, const float* dy, int N, float* gw, float* gb) {
     GemmJob j;
     memset(&j, 0, sizeof(j));
     j.a = Operand{x, 1, K, idx, 0};           // a(k, b) = X[b*K + k]
@@ -211,6 +222,7 @@ GemmJob bwd_weight_job(const float* x, const int32_t* idx, int B, int K, const f
 constexpr float kLogSqrt2Pi = 0.9189385175704956f;
 constexpr float kEntropyConst = 1.4189385175704956f;
 constexpr int kMaxActions = 4;
+constexpr int kMaxPersistentCtas = 1024;   // upper bound of the persistent learn() grid (one CTA per SM)
 
 struct HeadArgs {
     const float* h2;       // [B,H2] policy trunk output (post-relu)
@@ -238,14 +250,10 @@ struct HeadArgs {
 };
 
 // mode 0: log-prob only (old policy); mode 1: full training head; mode 2: predict (mu / sampled action, value)
+// one sample (row b) by one warp; MODE 1 adds its loss terms to vals[8]
 template <int MODE>
-__global__ void __launch_bounds__(256)
-ppo_head_kernel(const __grid_constant__ HeadArgs a) {
-    __shared__ float red[8][8];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * 8 + warp;
-    float vals[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (b < a.B) {
+__device__ __forceinline__ void head_row(const HeadArgs& a, int b, int lane, float* vals) {
+    {
         const float* h = a.h2 + (long long)b * a.H2;
         float pre[kMaxActions] = {0.f, 0.f, 0.f, 0.f};
         float vsum = 0.f;
@@ -326,36 +334,49 @@ ppo_head_kernel(const __grid_constant__ HeadArgs a) {
                 a.dh2[(long long)b * a.H2 + j] = h[j] > 0.f ? s : 0.f;
                 a.dg2[(long long)b * a.H2 + j] = a.g2[(long long)b * a.H2 + j] > 0.f ? dvv * a.wv[j] : 0.f;
             }
-            vals[0] = fminf(unclipped, clipped);
-            vals[1] = (v - ret) * (v - ret);
-            vals[2] = ratio;
+            vals[0] += fminf(unclipped, clipped);
+            vals[1] += (v - ret) * (v - ret);
+            vals[2] += ratio;
 #pragma unroll
             for (int k = 0; k < kMaxActions; ++k)
-                if (k < a.A) vals[3 + k] = dlogp * (diff[k] * diff[k] - 1.f);
-        }
-    }
-    if (MODE == 1) {
-        if (lane == 0)
-#pragma unroll
-            for (int k = 0; k < 8; ++k) red[warp][k] = vals[k];
-        __syncthreads();
-        if (threadIdx.x < 8) {
-            float s = 0.f;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-            a.partial[blockIdx.x * 8 + threadIdx.x] = s;
+                if (k < a.A) vals[3 + k] += dlogp * (diff[k] * diff[k] - 1.f);
         }
     }
 }
 
-// metrics[5] = policy_loss, value_loss, entropy_loss, loss, mean ratio; grads[logstd], value-bias etc.
-__global__ void ppo_finalize_kernel(const float* __restrict__ partial, int nblocks, int B, int A,
-                                    const float* __restrict__ logstd, float value_scale, float entropy_scale,
-                                    float* __restrict__ glogstd, float* __restrict__ metrics) {
-    __shared__ float tot[8];
+// CTA-level sum of the 8 warps' loss terms -> partial[block][8] (fixed order: deterministic)
+__device__ __forceinline__ void head_block_reduce(const float* vals, float (*red)[8], float* partial_out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) red[warp][k] = vals[k];
+    __syncthreads();
     if (threadIdx.x < 8) {
         float s = 0.f;
-        for (int i = 0; i < nblocks; ++i) s += partial[i * 8 + threadIdx.x];
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+        partial_out[threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+ppo_head_kernel(const __grid_constant__ HeadArgs a) {
+    __shared__ float red[8][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 8 + warp;
+    float vals[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (b < a.B) head_row<MODE>(a, b, lane, vals);
+    if (MODE == 1) head_block_reduce(vals, red, a.partial + blockIdx.x * 8);
+}
+
+// metrics[5] = policy_loss, value_loss, entropy_loss, loss, mean ratio; grads[logstd], value-bias etc.
+__device__ __forceinline__ void ppo_finalize(const float* partial, int nblocks, int B, int A, const float* logstd, float value_scale,
+                                             float entropy_scale, float* glogstd, float* metrics, float* tot /* shared [8] */) {
+    if (threadIdx.x < 8) {
+        float s = 0.f;
+        for (int i = 0; i < nblocks; ++i) s += __ldcg(partial + i * 8 + threadIdx.x);
         tot[threadIdx.x] = s;
     }
     __syncthreads();
@@ -373,6 +394,14 @@ __global__ void ppo_finalize_kernel(const float* __restrict__ partial, int nbloc
             metrics[0] = pl; metrics[1] = vl; metrics[2] = el; metrics[3] = -pl + vl - el; metrics[4] = tot[2] * inv_b;
         }
     }
+    __syncthreads();
+}
+
+__global__ void ppo_finalize_kernel(const float* __restrict__ partial, int nblocks, int B, int A,
+                                    const float* __restrict__ logstd, float value_scale, float entropy_scale,
+                                    float* __restrict__ glogstd, float* __restrict__ metrics) {
+    __shared__ float tot[8];
+    ppo_finalize(partial, nblocks, B, A, logstd, value_scale, entropy_scale, glogstd, metrics, tot);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -501,7 +530,7 @@ PpoPlan make_ppo_plan(void* ws, int64_t ws_bytes, const cpb_ppo_config* c, int m
     p.logp_old = a.take<float>(rows);
     p.dpre = a.take<float>(B * kMaxActions);
     p.dv = a.take<float>(B);
-    p.partial = a.take<float>((int64_t)cdiv(B, 8) * 8);
+    p.partial = a.take<float>((int64_t)(cdiv(B, 8) > kMaxPersistentCtas ? cdiv(B, 8) : kMaxPersistentCtas) * 8);
     p.ret32 = a.take<float>(rows);
     p.adv32 = a.take<float>(rows);
     p.gae_scratch = a.take<double>(rows);
@@ -592,6 +621,169 @@ int32_t run_loss_grad(const cpb_ppo_config* c, const PpoLayout& L, const PpoPlan
     gb.job[0] = bwd_weight_job(states, idx, B, S, dh1p, H1, grads + L.off[P_W1], grads + L.off[P_B1]);
     gb.job[1] = bwd_weight_job(states, idx, B, S, dh1v, H1, grads + L.off[P_V1], grads + L.off[P_VB1]);
     return launch_small_gemm(gb, 2, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The driver's whole update block as ONE persistent cooperative kernel (train.py:171-207 after GAE / theta_old):
+// num_epochs x ceil(T / batch) minibatch steps, each = forward (2 trunks x 2 layers) -> head + loss -> backward ->
+// TF-Adam, with grid-wide barriers between the dependent phases instead of ~9 kernel launches per minibatch (round 1:
+// ~330 launches of 5-30 us kernels, 5.3 ms per learn()).  One CTA per SM, 4 independent groups of 64 threads per CTA;
+// a phase's 32x32 output tiles are dealt round-robin to the 4 x gridDim groups; the arithmetic per tile is the
+// stand-alone small_gemm_kernel's (same gemm_tile), so the results are those of the launch-per-kernel path up to the
+// order in which the per-CTA loss partials are summed.
+// ---------------------------------------------------------------------------------------------
+struct LearnArgs {
+    cpb_ppo_config cfg;
+    PpoLayout L;
+    PpoPlan pl;
+    float* params; float* grads; float* adam_m; float* adam_v; float* adam_powers;
+    const float* lr_dev;
+    const float* states; const float* actions;
+    const int32_t* perms;
+    float* metrics;
+    int T, batch_size, num_epochs, nmb;
+};
+
+constexpr int kGroupsPerCta = 4;
+constexpr int kLearnThreads = kGroupsPerCta * 64;
+constexpr size_t kLearnSmem = (size_t)kGroupsPerCta * 2 * 2 * TK * (TS + 4) * sizeof(float);
+
+__device__ __forceinline__ int tiles_of(int n) { return (n + TS - 1) / TS; }
+
+template <int GATHER>
+__device__ __forceinline__ void run_phase(const GemmJob* jobs, int njobs, float* smem, int gid, int ngroups) {
+    const int group = threadIdx.x >> 6, gtid = threadIdx.x & 63;
+    float (*As)[TK][TS + 4] = reinterpret_cast<float (*)[TK][TS + 4]>(smem + (size_t)group * 2 * 2 * TK * (TS + 4));
+    float (*Bs)[TK][TS + 4] = As + 2;
+    int total = 0;
+    for (int j = 0; j < njobs; ++j) total += tiles_of(jobs[j].M) * tiles_of(jobs[j].N);
+    for (int t = gid; t < total; t += ngroups) {
+        int j = 0, r = t;
+        for (;; ++j) {
+            const int nt = tiles_of(jobs[j].M) * tiles_of(jobs[j].N);
+            if (r < nt) break;
+            r -= nt;
+        }
+        const int mt = tiles_of(jobs[j].M);
+        const int mi = r % mt, ni = r / mt;
+        gemm_tile<GATHER>(jobs[j], mi * TS, ni * TS, mi == 0, gtid, As, Bs,
+                          [group] { asm volatile("bar.sync %0, 64;" ::"r"(group + 1) : "memory"); });
+    }
+}
+
+__global__ void __launch_bounds__(kLearnThreads, 1)
+ppo_learn_persistent_kernel(const __grid_constant__ LearnArgs a) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) float learn_smem[];
+    __shared__ float red[8][8];
+    __shared__ float tot[8];
+    const cpb_ppo_config& c = a.cfg;
+    const PpoLayout& L = a.L;
+    const PpoPlan& pl = a.pl;
+    const int S = c.state_dim, H1 = c.hidden1, H2 = c.hidden2, A = c.num_actions;
+    const int ngroups = gridDim.x * kGroupsPerCta;
+    const int gid = blockIdx.x * kGroupsPerCta + (threadIdx.x >> 6);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* params = a.params;
+    float* grads = a.grads;
+
+    for (int e = 0; e < a.num_epochs; ++e)
+        for (int i = 0; i < a.nmb; ++i) {
+            const int begin = i * a.batch_size;
+            const int B = begin + a.batch_size <= a.T ? a.batch_size : a.T - begin;
+            const int32_t* idx = a.perms + (long long)e * a.T + begin;
+            float* mt = a.metrics ? a.metrics + ((long long)e * a.nmb + i) * 5 : nullptr;
+            float* h1p = pl.h1; float* h1v = pl.h1 + (long long)B * H1;
+            float* h2p = pl.h2; float* h2v = pl.h2 + (long long)B * H2;
+            float* dh2p = pl.dh2; float* dh2v = pl.dh2 + (long long)B * H2;
+            float* dh1p = pl.dh1; float* dh1v = pl.dh1 + (long long)B * H1;
+            GemmJob jobs[6];
+            // ---- forward, layer 1 and 2 of both trunks
+            jobs[0] = fwd_job(a.states, idx, B, S, params + L.off[P_W1], H1, params + L.off[P_B1], h1p, 1);
+            jobs[1] = fwd_job(a.states, idx, B, S, params + L.off[P_V1], H1, params + L.off[P_VB1], h1v, 1);
+            run_phase<1>(jobs, 2, learn_smem, gid, ngroups);
+            grid.sync();
+            jobs[0] = fwd_job(h1p, nullptr, B, H1, params + L.off[P_W2], H2, params + L.off[P_B2], h2p, 1);
+            jobs[1] = fwd_job(h1v, nullptr, B, H1, params + L.off[P_V2], H2, params + L.off[P_VB2], h2v, 1);
+            run_phase<0>(jobs, 2, learn_smem, gid, ngroups);
+            grid.sync();
+            // ---- head: one warp per sample, per-CTA partial loss sums
+            {
+                HeadArgs h;
+                h.h2 = h2p; h.g2 = h2v;
+                h.wm = params + L.off[P_WM]; h.bm = params + L.off[P_BM]; h.logstd = params + L.off[P_LOGSTD];
+                h.wv = params + L.off[P_WV]; h.bv = params + L.off[P_BV];
+                h.actions = a.actions; h.returns = pl.ret32; h.adv = pl.adv32; h.idx = idx;
+                h.logp_old_in = pl.logp_old; h.logp_old_gathered = 1;
+                h.B = B; h.H2 = H2; h.A = A;
+                for (int k = 0; k < kMaxActions; ++k) { h.low[k] = c.action_low[k]; h.high[k] = c.action_high[k]; }
+                h.eps_clip = c.epsilon; h.value_scale = c.value_scale; h.entropy_scale = c.entropy_scale;
+                h.logp_out = nullptr; h.mu_out = nullptr; h.v_out = nullptr;
+                h.dpre = pl.dpre; h.dv = pl.dv; h.dh2 = dh2p; h.dg2 = dh2v; h.partial = pl.partial;
+                h.noise = nullptr; h.action_out = nullptr;
+                float vals[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                for (int b = blockIdx.x * 8 + warp; b < B; b += gridDim.x * 8) head_row<1>(h, b, lane, vals);
+                head_block_reduce(vals, red, pl.partial + blockIdx.x * 8);
+            }
+            grid.sync();
+            // ---- loss metrics + logstd gradient (CTA 0), then everything that only needs the head's outputs
+            if (blockIdx.x == 0)
+                ppo_finalize(pl.partial, gridDim.x, B, A, params + L.off[P_LOGSTD], c.value_scale, c.entropy_scale, grads + L.off[P_LOGSTD], mt, tot);
+            jobs[0] = bwd_weight_job(h1p, nullptr, B, H1, dh2p, H2, grads + L.off[P_W2], grads + L.off[P_B2]);
+            jobs[1] = bwd_weight_job(h1v, nullptr, B, H1, dh2v, H2, grads + L.off[P_V2], grads + L.off[P_VB2]);
+            jobs[2] = bwd_data_job(dh2p, B, H2, params + L.off[P_W2], H1, h1p, dh1p);
+            jobs[3] = bwd_data_job(dh2v, B, H2, params + L.off[P_V2], H1, h1v, dh1v);
+            jobs[4] = bwd_weight_job(h2p, nullptr, B, H2, pl.dpre, A, grads + L.off[P_WM], grads + L.off[P_BM]);
+            jobs[5] = bwd_weight_job(h2v, nullptr, B, H2, pl.dv, 1, grads + L.off[P_WV], grads + L.off[P_BV]);
+            run_phase<0>(jobs, 6, learn_smem, gid, ngroups);
+            grid.sync();
+            jobs[0] = bwd_weight_job(a.states, idx, B, S, dh1p, H1, grads + L.off[P_W1], grads + L.off[P_B1]);
+            jobs[1] = bwd_weight_job(a.states, idx, B, S, dh1v, H1, grads + L.off[P_V1], grads + L.off[P_VB1]);
+            run_phase<2>(jobs, 2, learn_smem, gid, ngroups);
+            grid.sync();
+            // ---- TF ApplyAdam (the arithmetic of adam_kernel), beta powers advanced after the barrier
+            {
+                const float lr_t = a.lr_dev[0];
+                const float p0 = __ldcg(a.adam_powers), p1 = __ldcg(a.adam_powers + 1);
+                const float alpha = lr_t * sqrtf(1.f - p1) / (1.f - p0);
+                const float beta1 = 0.9f, beta2 = 0.999f, epsilon = 1e-8f;
+                const float omb1 = 1.f - beta1, omb2 = 1.f - beta2;
+                const long long n4 = L.total / 4;
+                float4* p4 = reinterpret_cast<float4*>(params);
+                const float4* g4 = reinterpret_cast<const float4*>(grads);
+                float4* m4 = reinterpret_cast<float4*>(a.adam_m);
+                float4* v4 = reinterpret_cast<float4*>(a.adam_v);
+                for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += (long long)gridDim.x * blockDim.x) {
+                    const float4 gv = __ldcg(g4 + k);
+                    float4 mv = m4[k], vv = v4[k], pv = p4[k];
+                    mv.x += (gv.x - mv.x) * omb1; mv.y += (gv.y - mv.y) * omb1; mv.z += (gv.z - mv.z) * omb1; mv.w += (gv.w - mv.w) * omb1;
+                    vv.x += (gv.x * gv.x - vv.x) * omb2; vv.y += (gv.y * gv.y - vv.y) * omb2;
+                    vv.z += (gv.z * gv.z - vv.z) * omb2; vv.w += (gv.w * gv.w - vv.w) * omb2;
+                    pv.x -= (mv.x * alpha) / (sqrtf(vv.x) + epsilon); pv.y -= (mv.y * alpha) / (sqrtf(vv.y) + epsilon);
+                    pv.z -= (mv.z * alpha) / (sqrtf(vv.z) + epsilon); pv.w -= (mv.w * alpha) / (sqrtf(vv.w) + epsilon);
+                    m4[k] = mv; v4[k] = vv; p4[k] = pv;
+                }
+            }
+            grid.sync();
+            if (blockIdx.x == 0 && threadIdx.x == 0) { a.adam_powers[0] *= 0.9f; a.adam_powers[1] *= 0.999f; }
+        }
+}
+
+int g_learn_grid = 0;      // co-resident CTAs of the persistent kernel (0: not initialised, -1: unavailable)
+
+int32_t learn_persistent_init() {
+    if (g_learn_grid != 0) return CPB_OK;
+    int dev = 0, sms = 0, coop = 0, per_sm = 0;
+    CPB_CUDA(cudaGetDevice(&dev));
+    CPB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CPB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    CPB_CUDA(cudaFuncSetAttribute(ppo_learn_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLearnSmem));
+    CPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ppo_learn_persistent_kernel, kLearnThreads, kLearnSmem));
+    const char* e = getenv("CPB_PPO_PERSISTENT");
+    const bool want = e == nullptr || atoi(e) != 0;
+    g_learn_grid = (coop && per_sm >= 1 && want) ? (sms < kMaxPersistentCtas ? sms : kMaxPersistentCtas) : -1;
+    return CPB_OK;
 }
 
 }  // namespace
@@ -703,6 +895,20 @@ int32_t cpb_ppo_learn(const cpb_ppo_config* cfg, float* params, float* params_ol
     CPB_TRY(run_old_logp(cfg, L, pl, params_old, states, actions, nullptr, T, s));
     CPB_TRY(launch_fill_zero(grads, L.total, s));
     const int nmb = cdiv(T, batch_size);
+    CPB_TRY(learn_persistent_init());
+    if (g_learn_grid > 0 && num_epochs > 0) {
+        // all minibatch steps in ONE cooperative launch
+        LearnArgs a;
+        memset(&a, 0, sizeof(a));
+        a.cfg = *cfg; a.L = L; a.pl = pl;
+        a.params = params; a.grads = grads; a.adam_m = adam_m; a.adam_v = adam_v; a.adam_powers = adam_powers; a.lr_dev = lr_dev;
+        a.states = states; a.actions = actions; a.perms = perms; a.metrics = metrics;
+        a.T = T; a.batch_size = batch_size; a.num_epochs = num_epochs; a.nmb = nmb;
+        void* args[] = {&a};
+        CPB_CUDA(cudaLaunchCooperativeKernel((void*)ppo_learn_persistent_kernel, dim3((unsigned)g_learn_grid), dim3(kLearnThreads), args, kLearnSmem, s));
+        CPB_LAUNCHED();
+        return CPB_OK;
+    }
     for (int e = 0; e < num_epochs; ++e)
         for (int i = 0; i < nmb; ++i) {
             const int begin = i * batch_size;

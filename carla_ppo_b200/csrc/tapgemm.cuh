@@ -90,6 +90,9 @@ struct TcWeightJob {
     int k, cb, cs;
     int N, C;                   // logical rows / reduction length per tap
     long long count;
+    int raw;                    // 1 (tc2 kernels): blocks ordered (n-tile y, tap, k-block): block index (y * ntaps + tap) * (C/32) + kc,
+                                // each block = [hi image | lo image] = 2*BN*32 floats (one bulk copy per k-block)
+    int ntaps;                  // taps of the operand (raw layout only)
 };
 // rows of the N axis handled per CTA tile (also fixes the block size of the stored operand)
 __host__ __device__ constexpr int tc_bn(int N) { return N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 32); }

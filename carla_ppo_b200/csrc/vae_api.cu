@@ -6,6 +6,7 @@
 
 #include "elementwise.cuh"
 #include "tapgemm.cuh"
+#include "tc2.cuh"
 #include "wgrad.cuh"
 
 namespace cpb {
@@ -59,6 +60,8 @@ int32_t ensure_init() {
         if (st == CPB_OK) st = wgrad_init();
         if (st == CPB_OK) st = tc_tapgemm_init();
         if (st == CPB_OK) st = tc_wgrad_init();
+        if (st == CPB_OK) st = tc2_tapgemm_init();
+        if (st == CPB_OK) st = tc2_wgrad_init();
         g_init_status[dev] = st;
         g_init_done[dev] = st == CPB_OK ? 1 : 2;
     }
@@ -200,6 +203,9 @@ static int64_t max_partial_floats(int B, int z) {
         {z, FEAT, (long long)B},                    // dense1
     };
     int64_t best = (int64_t)edge_wgrad_ctas(B) * 48 * C1;
+    // the tensor-core weight gradients run ONE wave of (i-tile, j-tile, split) CTAs with 128 x BN <= 128 tiles:
+    // splits * I * J <= 148 * 128 * 128 floats whatever the split rule (tc_wgrad.cu, tc2_wgrad.cu)
+    if (best < 148LL * 128 * 128) best = 148LL * 128 * 128;
     for (const P& p : ps) {
         int64_t n = (int64_t)wgrad_pick_splits(p.I, p.J, p.M) * p.I * p.J;
         if (n > best) best = n;
@@ -372,6 +378,7 @@ static int32_t tg(const char* label, const TapGemmParams& p, cudaStream_t s, int
     if (g_math_mode == 1 && p.wk_hi != nullptr && tl_lo_scratch != nullptr) {
         TapGemmParams q = scatter_k > 0 ? quad_from_scatter(p, scatter_k) : p;
         q.debug = tc_debug_flags();
+        if (tc2_tapgemm_supported(q, scatter_k)) return launch_tc2_tapgemm(q, scatter_k, s);     // TMA tensor maps, no lo planes
         q.src_lo = src_lo != nullptr ? src_lo : tl_lo_scratch;
         q.dst_lo = dst_lo;
         if (tc_tapgemm_supported(q)) {
@@ -394,7 +401,17 @@ static int32_t run_wgrad(const char* label, const float* big, int Wb, int pitch,
     for (int kh = 0; kh < k; ++kh) w.tap_off[kh] = (long long)kh * Wb * pitch;
     w.I = k * k * pitch; w.J = J;
     const long long M = (long long)B * Ho * Wo;
-    if (g_math_mode == 1 && tc_wgrad_supported(w.I, w.J, w.run)) {
+    // tc2_wgrad (MN-major operands by TMA) is parity-green but, like every SS-mode 3xTF32 kernel here, bound by the 128 B/clk
+    // of shared-memory bandwidth: its staging (copy-engine write + splitter read + write) costs 3 passes over each operand
+    // byte against 2 for the register path of tc_wgrad.cu, and measures 10-40 % slower (profiles/r2_cycle_accounting.md).
+    // Opt in with CPB_TC2_WGRAD=1; the unit tests exercise it through cpb_debug_tc_wgrad either way.
+    static const bool tc2_wg = [] { const char* e = getenv("CPB_TC2_WGRAD"); return e != nullptr && atoi(e) != 0; }();
+    if (g_math_mode == 1 && tc2_wg && tc2_wgrad_supported(w) && !(tc_debug_flags() & 32)) {
+        int bw, bh, bn; long long nboxes;
+        tc2_wgrad_plan(w, bw, bh, bn, nboxes);
+        w.splits = tc2_wgrad_pick_splits(w.I, w.J, nboxes);
+        CPB_TRY(launch_tc2_wgrad(w, s));
+    } else if (g_math_mode == 1 && tc_wgrad_supported(w.I, w.J, w.run)) {
         w.splits = tc_wgrad_pick_splits(w.I, w.J, M);
         w.m_per_split = align_up((M + w.splits - 1) / w.splits, 32);
         w.tc_variant = tc_debug_flags();
@@ -470,12 +487,14 @@ static int32_t relayout_weights(const VaePlan& pl, const VaeLayout& L, const flo
             TcWeightJob& j = w.jobs[w.njobs++];
             j.src_off = L.off[tensor]; j.dst_hi = pl.rl.tc[slot].f_hi; j.dst_lo = pl.rl.tc[slot].f_lo;
             j.mode = 1; j.k = k; j.cb = cb; j.cs = cs; j.N = cs; j.C = k * cb; j.count = n; w.total += n;
+            j.raw = tc2_enabled() ? 1 : 0; j.ntaps = k;
         }
         if (scatter) {
             TcWeightJob& j = w.jobs[w.njobs++];
             j.src_off = L.off[tensor]; j.dst_hi = pl.rl.tc[slot].t_hi; j.dst_lo = pl.rl.tc[slot].t_lo;
             const int win = (k + 1) / 2;
             j.mode = 2; j.k = k; j.cb = cb; j.cs = cs; j.N = 4 * cb; j.C = cs; j.count = (long long)win * win * 4 * cb * cs; w.total += j.count;
+            j.raw = tc2_enabled() ? 1 : 0; j.ntaps = win * win;
         }
     };
     // conv layers run gather-form forward / scatter-form dgrad; deconv layers the other way round
@@ -500,7 +519,7 @@ static int32_t run_encoder(const VaePlan& pl, const VaeLayout& L, const cpb_vae_
       CPB_TRY(launch_prep_frames(source, cfg->source_dtype, sscale, 3, (long long)B * NPIX, pl.xp, flags, 1, s)); }
     { ProfScope prof("conv1.fwd", s);
       CPB_TRY(launch_edge_gather(pl.xp, 3, params + L.off[T_CONV1_K], params + L.off[T_CONV1_B], nullptr, pl.a1,
-                                 g_math_mode == 1 ? pl.a1_lo : nullptr, B, s)); }
+                                 g_math_mode == 1 && !tc2_enabled() ? pl.a1_lo : nullptr, B, s)); }
     TapGemmParams p;
     p = gather_problem(pl.a1, B, H1, W1, C1, 4, params + L.off[T_CONV2_K], C2, params + L.off[T_CONV2_B], nullptr, pl.a2, 1,
                        pl.relayout + pl.rl.tc[TC_CONV2].f_hi, pl.relayout + pl.rl.tc[TC_CONV2].f_lo);
@@ -588,7 +607,7 @@ static int32_t run_backward(const VaePlan& pl, const VaeLayout& L, const cpb_vae
     CPB_TRY(launch_colsum(dlog, (long long)B * NPIX, 4, pl.ct, grads + L.off[T_DECONV4_B], cs, s));
     { ProfScope prof("deconv4.dgrad", s);
       CPB_TRY(launch_edge_gather(dlog, pl.ct, params + L.off[T_DECONV4_K], nullptr, pl.b3, pl.gA,
-                                 g_math_mode == 1 ? pl.gA_lo : nullptr, B, s)); }   // gA = g(b3 pre-activation)
+                                 g_math_mode == 1 && !tc2_enabled() ? pl.gA_lo : nullptr, B, s)); }   // gA = g(b3 pre-activation)
     TapGemmParams p;
     // ---- deconv3
     CPB_TRY(run_wgrad("deconv3.wgrad", pl.gA, W1, C1, (long long)H1 * W1 * C1, 5, pl.b2, B, H2, W2, C2, 5 * 5 * C1, 5 * 5 * C1,
@@ -696,10 +715,13 @@ int32_t cpb_debug_tc_gemm(const float* a, const float* bt, float* d, int32_t m, 
     memset(&w, 0, sizeof(w));
     w.njobs = 1; w.total = (long long)n * k;
     w.jobs[0].src_off = 0; w.jobs[0].dst_hi = 0; w.jobs[0].dst_lo = (long long)n * k; w.jobs[0].mode = 0; w.jobs[0].N = n; w.jobs[0].C = k; w.jobs[0].count = w.total;
-    CPB_TRY(launch_tc_weights(bt, scratch, w, s));
     TapGemmParams p = dense_problem(a, m, k, nullptr, n, nullptr, nullptr, d, 0);
     p.wk_hi = scratch; p.wk_lo = scratch + (long long)n * k;
     p.debug = tc_debug_flags();
+    const bool use_tc2 = tc2_tapgemm_supported(p, 0);
+    w.jobs[0].raw = use_tc2 ? 1 : 0; w.jobs[0].ntaps = 1;
+    CPB_TRY(launch_tc_weights(bt, scratch, w, s));
+    if (use_tc2) return launch_tc2_tapgemm(p, 0, s);
     float* lo = scratch + 2LL * n * k;
     p.src_lo = lo;
     CPB_TRY(launch_lo_plane(a, lo, (long long)m * k, s));
@@ -718,6 +740,10 @@ int32_t cpb_debug_tc_wgrad(const float* big, const float* small, float* out, int
     w.ntaps = 1; w.run = i; w.tap_off[0] = 0; w.I = i; w.J = j; w.tc_variant = variant;
     w.splits = 2;
     w.m_per_split = align_up(((long long)m + 1) / 2, 32);
+    if (tc2_wgrad_supported(w) && !(variant & 32)) {       // variant & 1: descriptor probe (LBO / SBO swapped); & 32: round-1 kernel
+        CPB_TRY(launch_tc2_wgrad(w, s));
+        return launch_reduce_partials(partial, w.splits, i, j, i, i, out, s);
+    }
     CPB_TRY(launch_tc_wgrad(w, s));
     return launch_reduce_partials(partial, w.splits, i, j, i, i, out, s);
 }
@@ -863,6 +889,32 @@ int32_t cpb_vae_train_step(const cpb_vae_config* cfg, float* params, float* grad
     // verify_range (vae/models.py:24-30, 89-90) is a tf.Assert the train op depends on: an out-of-range batch aborts the
     // reference's sess.run BEFORE ApplyAdam.  Same here: the update is skipped on the device when a flag bit is set.
     return cpb_adam_apply_guarded(params, grads, adam_m, adam_v, L.total, adam_powers, lr, nullptr, 0.9f, 0.999f, 1e-8f, flags, stream);
+}
+
+// state[b, 0:z] = latent[b, 0:z]; state[b, z:z+M] = measurements[b, 0:M]   (vae_common.py:59-61: np.append(encoded_state, measurements))
+__global__ void assemble_state_kernel(const float* __restrict__ latent, const float* __restrict__ meas, int batch, int z, int m,
+                                      float* __restrict__ state) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int w = z + m;
+    if (idx >= batch * w) return;
+    const int b = idx / w, c = idx - b * w;
+    state[idx] = c < z ? latent[b * z + c] : meas[b * m + (c - z)];
+}
+
+int32_t cpb_encode_predict(const cpb_vae_config* vae_cfg, const float* vae_params, const void* frames, const float* measurements,
+                           int32_t num_measurements, const cpb_ppo_config* ppo_cfg, const float* ppo_params, const float* noise,
+                           float* latent_tmp, float* state, float* action, float* value, int32_t* flags, void* vae_workspace,
+                           int64_t vae_workspace_bytes, void* ppo_workspace, int64_t ppo_workspace_bytes, void* stream) {
+    CPB_REQUIRE(vae_cfg && ppo_cfg && frames && latent_tmp && state && action && value, "encode_predict: NULL pointer");
+    CPB_REQUIRE(num_measurements >= 0 && (num_measurements == 0 || measurements != nullptr), "encode_predict: bad measurements");
+    CPB_REQUIRE(ppo_cfg->state_dim == vae_cfg->z_dim + num_measurements, "encode_predict: state_dim %d != z_dim %d + %d measurements",
+                ppo_cfg->state_dim, vae_cfg->z_dim, num_measurements);
+    const int B = vae_cfg->batch;
+    CPB_TRY(cpb_vae_encode(vae_cfg, vae_params, frames, latent_tmp, nullptr, flags, vae_workspace, vae_workspace_bytes, stream));
+    const int total = B * ppo_cfg->state_dim;
+    assemble_state_kernel<<<cdiv(total, 128), 128, 0, (cudaStream_t)stream>>>(latent_tmp, measurements, B, vae_cfg->z_dim, num_measurements, state);
+    CPB_LAUNCHED();
+    return cpb_ppo_forward(ppo_cfg, ppo_params, state, B, noise, action, value, ppo_workspace, ppo_workspace_bytes, stream);
 }
 
 static int64_t frame_bytes(int dtype, int channels) {

@@ -2,8 +2,8 @@
 evaluated by the float64 backward-scan CUDA kernel behind ``cpb_gae``.
 
 ``build_mlp`` / ``create_counter_variable`` / ``create_mean_metrics_from_dict`` (utils.py:25-43) are
-TensorFlow graph builders with no meaning outside TF; ``VideoRecorder`` (utils.py:9-23) is an OpenCV
-writer outside the hot-path scope.
+TensorFlow graph builders with no meaning outside TF; ``VideoRecorder`` (utils.py:9-23) is the same thin OpenCV
+writer (used by run_eval when a video file is requested).
 """
 from __future__ import annotations
 
@@ -33,3 +33,24 @@ def compute_gae(rewards, values, bootstrap_values, terminals, gamma, lam):
                            base + 16 * t_len, t_len, float(gamma), float(lam), out.data_ptr(), None, None,
                            _lib.current_stream_handle()), "cpb_gae")
     return out.cpu().numpy()
+
+
+class VideoRecorder:
+    """utils.py:9-23: AVI (MPEG) writer for the evaluation episodes; frames are RGB arrays."""
+
+    def __init__(self, filename, frame_size, fps=30):
+        import cv2
+        self._cv2 = cv2
+        self.video_writer = cv2.VideoWriter(filename, cv2.VideoWriter_fourcc(*"MPEG"), int(fps), (frame_size[1], frame_size[0]))
+
+    def add_frame(self, frame):
+        self.video_writer.write(self._cv2.cvtColor(frame, self._cv2.COLOR_RGB2BGR))
+
+    def release(self):
+        self.video_writer.release()
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass

@@ -208,6 +208,17 @@ int32_t cpb_ppo_learn(const cpb_ppo_config* cfg, float* params, float* params_ol
                       const int32_t* perms, float* metrics, void* workspace,
                       int64_t workspace_bytes, void* stream);
 
+/* One environment step of the reference's RL loop in ONE call with no host round trip in between (train.py:143 +
+ * vae_common.py:45-61 + ppo.py:231-251): frames [B,80,160,3] (uint8 or fp32, per vae_cfg->source_dtype) -> VAE mean ->
+ * state[b] = [latent(z) | measurements(M)] -> policy / value networks -> action (sampled with `noise`, or the mean when
+ * noise == NULL) and value.  latent_tmp: scratch [B,z]; state [B,z+M], action [B,A], value [B] are outputs. */
+int32_t cpb_encode_predict(const cpb_vae_config* vae_cfg, const float* vae_params, const void* frames,
+                           const float* measurements, int32_t num_measurements,
+                           const cpb_ppo_config* ppo_cfg, const float* ppo_params, const float* noise,
+                           float* latent_tmp, float* state, float* action, float* value, int32_t* flags,
+                           void* vae_workspace, int64_t vae_workspace_bytes,
+                           void* ppo_workspace, int64_t ppo_workspace_bytes, void* stream);
+
 /* Arithmetic used for the dense conv / transposed-conv contractions of the VAE (both are fp32-accurate):
  *   1 (default) tcgen05.mma kind::tf32 with the error-compensated 3xTF32 split, fp32 accumulators in TMEM;
  *   0           fp32 FMA (SIMT) tap-GEMM -- also used in mode 1 for the layers the tensor-core kernel does

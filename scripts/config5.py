@@ -32,8 +32,11 @@ def main():
     n_frames, batch, horizon = 100_000, 4096, 2048
     per_rank = -(-n_frames // world)
     tmp = tempfile.mkdtemp()
+    golden = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
     vae = ConvVAE((80, 160, 3), z_dim=64, loss_fn="mse", model_dir=os.path.join(tmp, "vae%d" % rank), seed=0, training=False)
     vae.init_session(init_logging=False)
+    zv = np.load(os.path.join(golden, "vae_rgb_ckpt232.npz"))
+    vae.set_weights({k: zv[k] for k in vae._names})                 # the reference's shipped rgb VAE (checkpoint-232)
     g = torch.Generator(device="cuda"); g.manual_seed(rank)
     frames = torch.randint(0, 256, (per_rank, 80, 160, 3), dtype=torch.uint8, device="cuda", generator=g)   # 3.84 GB / world
     latents = torch.empty(per_rank, 64, device="cuda")
@@ -61,6 +64,10 @@ def main():
             low = np.array([-1.0, 0.0], np.float32); high = np.array([1.0, 1.0], np.float32); shape = (2,)
         ppo = PPO((67,), Box(), learning_rate=1e-4, value_scale=1.0, model_dir=os.path.join(tmp, "ppo"), seed=0)
         ppo.init_session(init_logging=False)
+        zp = np.load(os.path.join(golden, "ppo_ckpt705.npz"))         # the reference's shipped agent (checkpoint-705)
+        ppo.set_weights({k: zp["policy/" + k] for k in ppo._names}, {k: zp["policy_old/" + k] for k in ppo._names},
+                        {k: zp["adam_m/" + k] for k in ppo._names}, {k: zp["adam_v/" + k] for k in ppo._names},
+                        (float(zp["beta1_power"]), float(zp["beta2_power"])))
         gen = torch.Generator(device="cuda"); gen.manual_seed(1)
         n_roll = (gathered.shape[0] // horizon)
         n_roll = min(n_roll, 48)
@@ -86,7 +93,8 @@ def main():
                           "encode_ms": float(enc_ms.item()), "encode_frames_per_s": world * per_rank / float(enc_ms.item()) * 1e3,
                           "rollouts": n_roll, "learn_ms_total": learn_ms, "ms_per_learn": learn_ms / n_roll,
                           "end_to_end_frames_per_s": n_used / total_ms * 1e3,
-                          "data": "synthetic uint8 frames resident in HBM, random-init weights"}))
+                          "allgather_bytes": int(world * per_rank * 64 * 4) if world > 1 else 0,
+                          "data": "synthetic uint8 frames resident in HBM; shipped VAE checkpoint-232 and agent checkpoint-705 weights"}))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
