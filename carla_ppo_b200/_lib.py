@@ -28,6 +28,10 @@ class VaeConfig(C.Structure):
                 ("loss_scale", C.c_float)]
 
 
+class MlpVaeConfig(C.Structure):
+    _fields_ = [("base", VaeConfig), ("enc1", C.c_int32), ("enc2", C.c_int32), ("dec1", C.c_int32), ("dec2", C.c_int32)]
+
+
 class PpoConfig(C.Structure):
     _fields_ = [("state_dim", C.c_int32), ("num_actions", C.c_int32), ("hidden1", C.c_int32),
                 ("hidden2", C.c_int32), ("action_low", C.c_float * 4), ("action_high", C.c_float * 4),
@@ -37,6 +41,7 @@ class PpoConfig(C.Structure):
 _P = C.c_void_p
 _i32, _i64, _f32, _f64 = C.c_int32, C.c_int64, C.c_float, C.c_double
 _VC = C.POINTER(VaeConfig)
+_MC = C.POINTER(MlpVaeConfig)
 _PC = C.POINTER(PpoConfig)
 
 # name -> (restype, argtypes); must list every symbol of include/carla_ppo_b200.h
@@ -56,6 +61,14 @@ PROTOTYPES = {
     "cpb_vae_train_step": (_i32, [_VC, _P, _P, _P, _P, _P, _f32, _P, _P, _P, _P, _P, _P, _i64, _P]),
     "cpb_vae_staging_bytes": (_i64, [_VC]),
     "cpb_vae_train_step_host": (_i32, [_VC, _P, _P, _P, _P, _P, _f32, _P, _P, _P, _P, _P, _P, _i64, _P, _i64, _P]),
+    "cpb_mlpvae_num_tensors": (_i32, []),
+    "cpb_mlpvae_tensor_name": (C.c_char_p, [_i32]),
+    "cpb_mlpvae_layout": (_i32, [_MC, _P, _P, _P, _P]),
+    "cpb_mlpvae_workspace_bytes": (_i64, [_MC, _i32]),
+    "cpb_mlpvae_encode": (_i32, [_MC, _P, _P, _P, _P, _P, _P, _i64, _P]),
+    "cpb_mlpvae_decode": (_i32, [_MC, _P, _P, _P, _P, _i64, _P]),
+    "cpb_mlpvae_forward": (_i32, [_MC, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _i64, _P]),
+    "cpb_mlpvae_loss_grad": (_i32, [_MC, _P, _P, _P, _P, _P, _P, _P, _P, _i64, _P]),
     "cpb_ppo_num_tensors": (_i32, []),
     "cpb_ppo_tensor_name": (C.c_char_p, [_i32]),
     "cpb_ppo_layout": (_i32, [_PC, _P, _P, _P, _P]),

@@ -28,6 +28,26 @@ __global__ void prep_frames_kernel(const T* __restrict__ src, float scale, long 
     }
 }
 
+// flat variant (MlpVAE: tf.layers.flatten of the NHWC frame, no channel padding): dst[i] = src[i] * scale, range check
+template <typename T>
+__global__ void prep_flat_kernel(const T* __restrict__ src, float scale, long long n, float* __restrict__ dst, int32_t* flags, int flag_bit) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool bad = false;
+    if (i < n) {
+        const float x = (float)src[i] * scale;
+        dst[i] = x;
+        bad = !(x >= 0.f && x <= 1.f);
+    }
+    if (flags != nullptr && __any_sync(0xffffffffu, bad)) {
+        if ((threadIdx.x & 31) == 0) atomicOr(flags, flag_bit);
+    }
+}
+
+__global__ void sigmoid_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = 1.f / (1.f + expf(-x[i]));
+}
+
 // ------------------------------------------------------------------------------------------
 // output layer: conv2d_transpose 4x4 s2, 32 -> CT channels.
 // ------------------------------------------------------------------------------------------
@@ -446,6 +466,39 @@ int32_t launch_recon_loss(const float* logits_p, const float* target_p, int batc
         case CPB_LOSS_BCE_V2: return launch_recon_loss_t<CPB_LOSS_BCE_V2>(logits_p, target_p, batch, ct, gscale, frame_loss, dlogits_p, stream);
     }
     CPB_REQUIRE(false, "recon_loss: unknown loss_type %d", loss_type);
+}
+
+int32_t launch_prep_flat(const void* src, int dtype, float scale, long long n, float* dst, int32_t* flags, int flag_bit, cudaStream_t stream) {
+    if (n == 0) return CPB_OK;
+    const unsigned blocks = (unsigned)cdiv(n, 256);
+    if (dtype == CPB_FRAME_F32) prep_flat_kernel<float><<<blocks, 256, 0, stream>>>((const float*)src, scale, n, dst, flags, flag_bit);
+    else if (dtype == CPB_FRAME_U8) prep_flat_kernel<uint8_t><<<blocks, 256, 0, stream>>>((const uint8_t*)src, scale, n, dst, flags, flag_bit);
+    else CPB_REQUIRE(false, "prep_flat: unknown frame dtype %d", dtype);
+    CPB_LAUNCHED();
+    return CPB_OK;
+}
+
+int32_t launch_sigmoid(const float* x, float* y, long long n, cudaStream_t stream) {
+    if (n == 0) return CPB_OK;
+    sigmoid_kernel<<<cdiv(n, 256), 256, 0, stream>>>(x, y, n);
+    CPB_LAUNCHED();
+    return CPB_OK;
+}
+
+// unpadded [B, n] logits / targets (n % 4 == 0): every float4 lane is a real element (the CT = 4 instantiation)
+int32_t launch_recon_loss_flat(const float* logits, const float* target, int batch, int n, int loss_type, float gscale,
+                               float* frame_loss, float* dlogits, cudaStream_t stream) {
+    CPB_REQUIRE(n % 4 == 0, "recon_loss_flat: row length must be a multiple of 4");
+    if (batch == 0) return CPB_OK;
+    const int n4 = n / 4;
+    switch (loss_type) {
+        case CPB_LOSS_MSE: recon_loss_kernel<CPB_LOSS_MSE, 4><<<batch, 256, 0, stream>>>((const float4*)logits, (const float4*)target, n4, gscale, frame_loss, (float4*)dlogits); break;
+        case CPB_LOSS_BCE: recon_loss_kernel<CPB_LOSS_BCE, 4><<<batch, 256, 0, stream>>>((const float4*)logits, (const float4*)target, n4, gscale, frame_loss, (float4*)dlogits); break;
+        case CPB_LOSS_BCE_V2: recon_loss_kernel<CPB_LOSS_BCE_V2, 4><<<batch, 256, 0, stream>>>((const float4*)logits, (const float4*)target, n4, gscale, frame_loss, (float4*)dlogits); break;
+        default: CPB_REQUIRE(false, "recon_loss_flat: unknown loss_type %d", loss_type);
+    }
+    CPB_LAUNCHED();
+    return CPB_OK;
 }
 
 int32_t launch_finalize_losses(const float* frame_loss, const float* kl_rows, int batch, float scale,

@@ -37,6 +37,13 @@ int32_t launch_reparam_bwd(const float* heads, const float* eps, const float* gz
 int32_t launch_recon_loss(const float* logits_p, const float* target_p, int batch, int ct, int loss_type,
                           float gscale, float* frame_loss, float* dlogits_p, cudaStream_t stream);
 
+// MlpVAE (flattened frames, no channel padding): dst[i] = src[i] * scale with the verify_range flag; y = sigmoid(x);
+// reconstruction loss on unpadded [B, n] rows
+int32_t launch_prep_flat(const void* src, int dtype, float scale, long long n, float* dst, int32_t* flags, int flag_bit, cudaStream_t stream);
+int32_t launch_sigmoid(const float* x, float* y, long long n, cudaStream_t stream);
+int32_t launch_recon_loss_flat(const float* logits, const float* target, int batch, int n, int loss_type, float gscale,
+                               float* frame_loss, float* dlogits, cudaStream_t stream);
+
 // losses[0] = scale * mean(frame_loss), losses[1] = scale * mean(kl_rows)
 int32_t launch_finalize_losses(const float* frame_loss, const float* kl_rows, int batch, float scale,
                                float* losses, cudaStream_t stream);
@@ -55,7 +62,7 @@ struct RelayoutJob {
     int rows_pad;
     long long count;              // destination elements
 };
-constexpr int kMaxRelayoutJobs = 12;
+constexpr int kMaxRelayoutJobs = 12;   // (MlpVAE uses 6)
 struct RelayoutTable {
     int njobs;
     long long total;

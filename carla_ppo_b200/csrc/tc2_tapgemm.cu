@@ -33,7 +33,13 @@ struct Tc2Cfg {
     static constexpr int SLICE = BN / 2 < 32 ? BN / 2 : 32;                      // columns transposed per epilogue pass
     static constexpr int STAGING_BYTES = 8 * 32 * SLICE * 4;                     // 8 drain warps x [32 rows x SLICE floats]
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024;
-    static constexpr int TMEM_COLS = 4 * BN;
+    // TSA (BN <= 64): the A operand of both MMAs is read from TENSOR MEMORY, not shared memory: the splitters move each
+    // k-block's rows (raw = hi, and lo) into TMEM columns with tcgen05.st, 2 x 32 columns per stage, next to the accumulators
+    static constexpr bool TSA = BN <= 64;
+    static constexpr int ACC_COLS = 4 * BN;
+    static constexpr int TMEM_NEED = ACC_COLS + (TSA ? STAGES * 64 : 0);
+    static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
+    static_assert(TMEM_NEED <= 512, "tensor memory budget");
 };
 constexpr int kPrefetchKb = 12;   // k-blocks the L2 prefetch runs ahead of the shared-memory copies
 constexpr int CHUNK_KB = 4;
@@ -79,6 +85,28 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask, boo
                      ::"r"(smem_u32(bar)), "h"(mask) : "memory");
     else
         umma_commit(bar);
+}
+
+// 32 lanes x 32 consecutive 32-bit columns <- 32 registers per thread (this warp's lane quarter)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]),
+          "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]), "f"(v[18]), "f"(v[19]),
+          "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]),
+          "f"(v[30]), "f"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] x B[smem descriptor]   (A: lane = row, one 32-bit column per k)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 
 #define TC2_PROF(slot) do { if constexpr (PROF) { const long long now_ = clock64(); prof[slot] += now_ - tlast; tlast = now_; } } while (0)
@@ -186,7 +214,22 @@ tc2_tapgemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
                 const int s = g % STAGES;
                 mbar_wait(&full_bar[s], (uint32_t)((g / STAGES) & 1));
                 const uint32_t stage = smem_base + s * STAGE_BYTES;
-                if (!(p.debug & 4)) {
+                if constexpr (Cfg::TSA) {
+                    // row tl of the tile (8 swizzled 16-byte chunks, conflict-free per quarter-warp) -> registers -> TMEM:
+                    // columns [0,32) of the stage's slot hold a_hi (the raw values), [32,64) hold a_lo
+                    float v[32], l[32];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[4 * c]), "=f"(v[4 * c + 1]), "=f"(v[4 * c + 2]), "=f"(v[4 * c + 3])
+                                     : "r"(stage + (uint32_t)(tl * 128 + ((c ^ (tl & 7)) << 4))));
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) { float h; split_tf32(v[i], h, l[i]); }
+                    const uint32_t ta = tmem_base + ((uint32_t)((warp - kSplitWarp0) * 32) << 16) + (uint32_t)(Cfg::ACC_COLS + s * 64);
+                    tmem_st32(ta, v);
+                    tmem_st32(ta + 32u, l);
+                    tmem_st_wait();
+                    tc_fence_before();
+                } else if (!(p.debug & 4)) {
 #pragma unroll
                     for (int i = 0; i < A_TILE_BYTES / 16 / kSplitThreads; ++i) {
                         const uint32_t a = stage + (uint32_t)((tl + i * kSplitThreads) * 16);
@@ -227,12 +270,22 @@ tc2_tapgemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
                     const uint64_t b_hi = make_desc(stage + 2 * A_TILE_BYTES);     // [b_hi | b_lo] adjacent: one N = 2*BN operand
                     const uint32_t d_main = tmem_base + (uint32_t)(b * 2 * BN);
                     const uint32_t d_cross = d_main + (uint32_t)BN;
-                    if (!(p.debug & 1))
+                    if constexpr (Cfg::TSA) {
+                        const uint32_t ta = tmem_base + (uint32_t)(Cfg::ACC_COLS + s * 64);
+                        if (!(p.debug & 1))
 #pragma unroll
-                    for (int ks = 0; ks < TBK / 8; ++ks) {
-                        const uint64_t adv = (uint64_t)(ks * 2);
-                        umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc2, ((kb % CHUNK_KB) | ks) != 0 ? 1u : 0u);
-                        umma_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, 1u);
+                        for (int ks = 0; ks < TBK / 8; ++ks) {
+                            const uint64_t adv = (uint64_t)(ks * 2);
+                            umma_tf32_ts(d_main, ta + (uint32_t)(ks * 8), b_hi + adv, idesc2, ((kb % CHUNK_KB) | ks) != 0 ? 1u : 0u);
+                            umma_tf32_ts(d_cross, ta + 32u + (uint32_t)(ks * 8), b_hi + adv, idesc, 1u);
+                        }
+                    } else if (!(p.debug & 1)) {
+#pragma unroll
+                        for (int ks = 0; ks < TBK / 8; ++ks) {
+                            const uint64_t adv = (uint64_t)(ks * 2);
+                            umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc2, ((kb % CHUNK_KB) | ks) != 0 ? 1u : 0u);
+                            umma_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, 1u);
+                        }
                     }
                     umma_commit_mc(&empty_bar[s], cl_mask, CS > 1);
                     if (kb % CHUNK_KB == CHUNK_KB - 1 || kb == nkb - 1) { umma_commit(&chunk_bar[b]); ++gc; }

@@ -1,6 +1,7 @@
 // ConvVAE orchestration behind the C ABI (include/carla_ppo_b200.h).
 // Replaces the TF graph built by reference vae/models.py:85-142 + 249-266 and the sess.run calls of
 // VAE.encode / generate_from_latent / reconstruct / evaluate / train_one_epoch (:188-231).
+#include <algorithm>
 #include <mutex>
 #include <stdarg.h>
 
@@ -682,6 +683,193 @@ static int32_t run_backward(const VaePlan& pl, const VaeLayout& L, const cpb_vae
     return CPB_OK;
 }
 
+
+// =============================================================================================
+// MlpVAE (reference vae/models.py:271-299): flatten -> dense E1 relu -> dense E2 relu -> [mean | logstd_sq] -> sample ->
+// dense D1 relu -> dense D2 relu -> dense 12800*Ct -> logits.  Same loss / sampling / Adam kernels as the ConvVAE; all
+// seven layers run on the fp32 SIMT tap-GEMM (dense form) and the SIMT weight-gradient kernel.
+// =============================================================================================
+enum MlpTensor { M_E1_K, M_E1_B, M_E2_K, M_E2_B, M_MEAN_K, M_MEAN_B, M_LOGVAR_K, M_LOGVAR_B, M_D1_K, M_D1_B, M_D2_K, M_D2_B, M_D3_K, M_D3_B, M_COUNT };
+static const char* kMlpNames[M_COUNT] = {
+    "encoder/dense/kernel", "encoder/dense/bias", "encoder/dense_1/kernel", "encoder/dense_1/bias",
+    "mean/kernel", "mean/bias", "logstd_sqare/kernel", "logstd_sqare/bias",
+    "decoder/dense/kernel", "decoder/dense/bias", "decoder/dense_1/kernel", "decoder/dense_1/bias",
+    "decoder/dense_2/kernel", "decoder/dense_2/bias"};
+
+struct MlpLayout { int64_t off[M_COUNT], size[M_COUNT]; int32_t shape[M_COUNT][2]; int64_t total; };
+
+static int32_t check_mlp_cfg(const cpb_mlpvae_config* c) {
+    CPB_REQUIRE(c != nullptr, "mlp cfg is NULL");
+    CPB_TRY(check_cfg(&c->base));
+    for (int v : {c->enc1, c->enc2, c->dec1, c->dec2})
+        CPB_REQUIRE(v >= 32 && v % 32 == 0 && v <= 8192, "MlpVAE hidden sizes must be multiples of 32 in [32, 8192], got %d", v);
+    return CPB_OK;
+}
+
+static MlpLayout make_mlp_layout(const cpb_mlpvae_config* c) {
+    const int IN = geo::NPIX * 3, OUT = geo::NPIX * c->base.target_channels, z = c->base.z_dim;
+    const int shp[M_COUNT][2] = {{IN, c->enc1}, {c->enc1, 0}, {c->enc1, c->enc2}, {c->enc2, 0}, {c->enc2, z}, {z, 0}, {c->enc2, z}, {z, 0},
+                                 {z, c->dec1}, {c->dec1, 0}, {c->dec1, c->dec2}, {c->dec2, 0}, {c->dec2, OUT}, {OUT, 0}};
+    // the two head kernels (and biases) adjacent: both heads run as one y-batched dense problem
+    static const int order[M_COUNT] = {M_E1_K, M_E1_B, M_E2_K, M_E2_B, M_MEAN_K, M_LOGVAR_K, M_MEAN_B, M_LOGVAR_B,
+                                       M_D1_K, M_D1_B, M_D2_K, M_D2_B, M_D3_K, M_D3_B};
+    MlpLayout L;
+    for (int i = 0; i < M_COUNT; ++i) { L.shape[i][0] = shp[i][0]; L.shape[i][1] = shp[i][1]; L.size[i] = (int64_t)shp[i][0] * (shp[i][1] ? shp[i][1] : 1); }
+    int64_t o = 0;
+    for (int i = 0; i < M_COUNT; ++i) { L.off[order[i]] = o; o += align_up(L.size[order[i]], 64); }
+    L.total = o;
+    return L;
+}
+
+struct MlpPlan {
+    int B, IN, OUT, z, e1, e2, d1, d2;
+    float *x, *y, *h1, *h2, *heads, *zbuf, *kl_rows, *kl_active, *frame_loss, *g1, *g2, *logits;
+    float *ga, *gb, *gz, *gheads, *partial, *colsum, *wT, *ksplit;
+    int64_t tE2, tHeads, tD1, tD2, tD3;      // float offsets of the transposed kernels inside wT
+    int64_t bytes;
+    bool ok;
+};
+
+static MlpPlan make_mlp_plan(void* ws, int64_t ws_bytes, const cpb_mlpvae_config* c, int mode) {
+    MlpPlan p;
+    memset(&p, 0, sizeof(p));
+    const int64_t b = c->base.batch;
+    p.B = (int)b; p.IN = geo::NPIX * 3; p.OUT = geo::NPIX * c->base.target_channels; p.z = c->base.z_dim;
+    p.e1 = c->enc1; p.e2 = c->enc2; p.d1 = c->dec1; p.d2 = c->dec2;
+    Arena a(ws, ws_bytes);
+    p.x = a.take<float>(b * p.IN);
+    p.h1 = a.take<float>(b * p.e1);
+    p.h2 = a.take<float>(b * p.e2);
+    p.heads = a.take<float>(2 * b * p.z);
+    p.ksplit = a.take<float>((int64_t)kMaxKSplit * 2 * b * p.z);
+    if (mode >= CPB_WS_FORWARD) {
+        p.y = a.take<float>(b * p.OUT);
+        p.zbuf = a.take<float>(b * p.z);
+        p.kl_rows = a.take<float>(b); p.kl_active = a.take<float>(b); p.frame_loss = a.take<float>(b);
+        p.g1 = a.take<float>(b * p.d1);
+        p.g2 = a.take<float>(b * p.d2);
+        p.logits = a.take<float>(b * p.OUT);
+    }
+    if (mode >= CPB_WS_TRAIN) {
+        const int64_t widest = std::max<int64_t>(std::max(p.e1, p.e2), std::max(p.d1, p.d2));
+        p.ga = a.take<float>(b * widest);
+        p.gb = a.take<float>(b * widest);
+        p.gz = a.take<float>(b * p.z);
+        p.gheads = a.take<float>(2 * b * p.z);
+        int64_t o = 0;
+        auto take = [&](int64_t n) { int64_t at = o; o += align_up(n, 64); return at; };
+        p.tE2 = take((int64_t)p.e1 * p.e2); p.tHeads = take(2LL * p.e2 * p.z); p.tD1 = take((int64_t)p.z * p.d1);
+        p.tD2 = take((int64_t)p.d1 * p.d2); p.tD3 = take((int64_t)p.d2 * p.OUT);
+        p.wT = a.take<float>(o);
+        struct P { int I, J; };
+        const P ps[] = {{p.IN, p.e1}, {p.e1, p.e2}, {p.e2, p.z}, {p.z, p.d1}, {p.d1, p.d2}, {p.d2, p.OUT}};
+        int64_t best = 0;
+        for (const P& q : ps) best = std::max<int64_t>(best, (int64_t)wgrad_pick_splits(q.I, q.J, b) * q.I * q.J);
+        p.partial = a.take<float>(best);
+        p.colsum = a.take<float>(colsum_scratch_floats(b, p.OUT) + colsum_scratch_floats(b, (int)widest));
+    }
+    p.bytes = a.off;
+    p.ok = ws == nullptr || !a.overflow;
+    return p;
+}
+
+static int32_t mlp_encoder(const MlpPlan& pl, const MlpLayout& L, const cpb_mlpvae_config* c, const float* params, const void* source,
+                           int32_t* flags, cudaStream_t s) {
+    const float sscale = c->base.source_dtype == CPB_FRAME_U8 ? 1.f / 255.f : 1.f;
+    CPB_TRY(launch_prep_flat(source, c->base.source_dtype, sscale, (long long)pl.B * pl.IN, pl.x, flags, 1, s));
+    TapGemmParams p = dense_problem(pl.x, pl.B, pl.IN, params + L.off[M_E1_K], pl.e1, params + L.off[M_E1_B], nullptr, pl.h1, 1);
+    CPB_TRY(launch_tapgemm(p, s));
+    p = dense_problem(pl.h1, pl.B, pl.e1, params + L.off[M_E2_K], pl.e2, params + L.off[M_E2_B], nullptr, pl.h2, 1);
+    CPB_TRY(launch_tapgemm(p, s));
+    p = dense_problem(pl.h2, pl.B, pl.e2, params + L.off[M_MEAN_K], pl.z, params + L.off[M_MEAN_B], nullptr, pl.heads, 0);
+    p.ybatch = 2;
+    p.w_ystride = L.off[M_LOGVAR_K] - L.off[M_MEAN_K];
+    p.bias_ystride = L.off[M_LOGVAR_B] - L.off[M_MEAN_B];
+    p.dst_ystride = (long long)pl.B * pl.z;
+    return launch_tapgemm(p, s);
+}
+
+static int32_t mlp_decoder(const MlpPlan& pl, const MlpLayout& L, const float* params, const float* zsrc, float* logits, cudaStream_t s) {
+    TapGemmParams p = dense_problem(zsrc, pl.B, pl.z, params + L.off[M_D1_K], pl.d1, params + L.off[M_D1_B], nullptr, pl.g1, 1);
+    CPB_TRY(launch_tapgemm(p, s));
+    p = dense_problem(pl.g1, pl.B, pl.d1, params + L.off[M_D2_K], pl.d2, params + L.off[M_D2_B], nullptr, pl.g2, 1);
+    CPB_TRY(launch_tapgemm(p, s));
+    p = dense_problem(pl.g2, pl.B, pl.d2, params + L.off[M_D3_K], pl.OUT, params + L.off[M_D3_B], nullptr, logits, 0);
+    return launch_tapgemm(p, s);
+}
+
+static int32_t mlp_forward_loss(const MlpPlan& pl, const MlpLayout& L, const cpb_mlpvae_config* c, const float* params, const void* source,
+                                const void* target, const float* eps, bool want_dlogits, int32_t* flags, cudaStream_t s) {
+    CPB_TRY(mlp_encoder(pl, L, c, params, source, flags, s));
+    CPB_TRY(launch_reparam(pl.heads, eps, pl.B, pl.z, c->base.kl_tolerance, pl.zbuf, pl.kl_rows, pl.kl_active, s));
+    CPB_TRY(mlp_decoder(pl, L, params, pl.zbuf, pl.logits, s));
+    const float* y = pl.y;
+    if (target == source && c->base.target_channels == 3 && c->base.target_dtype == c->base.source_dtype &&
+        (c->base.target_dtype == CPB_FRAME_F32 || c->base.target_u8_scale == 1.f / 255.f)) {
+        y = pl.x;
+    } else {
+        const float tscale = c->base.target_dtype == CPB_FRAME_U8 ? c->base.target_u8_scale : 1.f;
+        CPB_TRY(launch_prep_flat(target, c->base.target_dtype, tscale, (long long)pl.B * pl.OUT, pl.y, flags, 2, s));
+    }
+    return launch_recon_loss_flat(pl.logits, y, pl.B, pl.OUT, c->base.loss_type, c->base.loss_scale / (float)pl.B, pl.frame_loss,
+                                  want_dlogits ? pl.logits : nullptr, s);
+}
+
+static int32_t mlp_backward(const MlpPlan& pl, const MlpLayout& L, const cpb_mlpvae_config* c, const float* params, const float* eps,
+                            float* grads, cudaStream_t s) {
+    const int B = pl.B, z = pl.z;
+    float* dlog = pl.logits;
+    float* cs = pl.colsum;
+    CPB_TRY(launch_fill_zero(grads, L.total, s));
+    // transposed kernels for the data gradients ([in,out] -> [out,in]); the two head kernels are adjacent (2 "taps")
+    RelayoutTable t;
+    memset(&t, 0, sizeof(t));
+    auto add = [&](int64_t src, int64_t dst, int taps, int rows, int cols) {
+        RelayoutJob& j = t.jobs[t.njobs++];
+        j.src_off = src; j.dst_off = dst; j.taps = taps; j.rows = rows; j.cols = cols; j.mode = 0; j.rows_pad = 0;
+        j.count = (long long)taps * rows * cols; t.total += j.count;
+    };
+    add(L.off[M_E2_K], pl.tE2, 1, pl.e1, pl.e2);
+    add(L.off[M_MEAN_K], pl.tHeads, 2, pl.e2, z);
+    add(L.off[M_D1_K], pl.tD1, 1, z, pl.d1);
+    add(L.off[M_D2_K], pl.tD2, 1, pl.d1, pl.d2);
+    add(L.off[M_D3_K], pl.tD3, 1, pl.d2, pl.OUT);
+    CPB_TRY(launch_relayout(params, pl.wT, t, s));
+    TapGemmParams p;
+    // ---- decoder
+    CPB_TRY(run_dense_wgrad("mlp.wgrad", pl.g2, pl.d2, dlog, B, pl.OUT, pl.partial, grads + L.off[M_D3_K], s));
+    CPB_TRY(launch_colsum(dlog, B, pl.OUT, pl.OUT, grads + L.off[M_D3_B], cs, s));
+    p = dense_problem(dlog, B, pl.OUT, pl.wT + pl.tD3, pl.d2, nullptr, pl.g2, pl.ga, 0);                       // ga = g(g2 pre-activation)
+    CPB_TRY(launch_tapgemm(p, s));
+    CPB_TRY(run_dense_wgrad("mlp.wgrad", pl.g1, pl.d1, pl.ga, B, pl.d2, pl.partial, grads + L.off[M_D2_K], s));
+    CPB_TRY(launch_colsum(pl.ga, B, pl.d2, pl.d2, grads + L.off[M_D2_B], cs, s));
+    p = dense_problem(pl.ga, B, pl.d2, pl.wT + pl.tD2, pl.d1, nullptr, pl.g1, pl.gb, 0);                         // gb = g(g1 pre-activation)
+    CPB_TRY(launch_tapgemm(p, s));
+    CPB_TRY(run_dense_wgrad("mlp.wgrad", pl.zbuf, z, pl.gb, B, pl.d1, pl.partial, grads + L.off[M_D1_K], s));
+    CPB_TRY(launch_colsum(pl.gb, B, pl.d1, pl.d1, grads + L.off[M_D1_B], cs, s));
+    p = dense_problem(pl.gb, B, pl.d1, pl.wT + pl.tD1, z, nullptr, nullptr, pl.gz, 0);
+    CPB_TRY(launch_tapgemm(p, s));
+    // ---- sampling + KL, heads
+    CPB_TRY(launch_reparam_bwd(pl.heads, eps, pl.gz, pl.kl_active, B, z, c->base.beta * c->base.loss_scale / (float)B, pl.gheads, s));
+    CPB_TRY(run_dense_wgrad("mlp.wgrad", pl.h2, pl.e2, pl.gheads, B, z, pl.partial, grads + L.off[M_MEAN_K], s));
+    CPB_TRY(run_dense_wgrad("mlp.wgrad", pl.h2, pl.e2, pl.gheads + (long long)B * z, B, z, pl.partial, grads + L.off[M_LOGVAR_K], s));
+    CPB_TRY(launch_colsum(pl.gheads, B, z, z, grads + L.off[M_MEAN_B], cs, s));
+    CPB_TRY(launch_colsum(pl.gheads + (long long)B * z, B, z, z, grads + L.off[M_LOGVAR_B], cs, s));
+    p = dense_problem(pl.gheads, B, z, pl.wT + pl.tHeads, pl.e2, nullptr, pl.h2, pl.ga, 0);
+    p.cls[0].ntaps = 2;
+    p.cls[0].taps[1].dy = p.cls[0].taps[1].dx = 0;
+    p.cls[0].taps[1].src_off = (long long)B * z;
+    p.cls[0].taps[1].w_off = (long long)z * pl.e2;
+    CPB_TRY(launch_tapgemm(p, s));                                                                               // ga = g(h2 pre-activation)
+    // ---- encoder
+    CPB_TRY(run_dense_wgrad("mlp.wgrad", pl.h1, pl.e1, pl.ga, B, pl.e2, pl.partial, grads + L.off[M_E2_K], s));
+    CPB_TRY(launch_colsum(pl.ga, B, pl.e2, pl.e2, grads + L.off[M_E2_B], cs, s));
+    p = dense_problem(pl.ga, B, pl.e2, pl.wT + pl.tE2, pl.e1, nullptr, pl.h1, pl.gb, 0);                         // gb = g(h1 pre-activation)
+    CPB_TRY(launch_tapgemm(p, s));
+    CPB_TRY(run_dense_wgrad("mlp.wgrad", pl.x, pl.IN, pl.gb, B, pl.e1, pl.partial, grads + L.off[M_E1_K], s));
+    return launch_colsum(pl.gb, B, pl.e1, pl.e1, grads + L.off[M_E1_B], cs, s);
+}
+
 }  // namespace cpb
 
 // =============================================================================================
@@ -963,6 +1151,82 @@ int32_t cpb_vae_train_step_host(const cpb_vae_config* cfg, float* params, float*
     losses_host[1] = host_out[1];
     if (flags_host) memcpy(flags_host, &host_out[2], 4);
     return CPB_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------------- MlpVAE */
+int32_t cpb_mlpvae_num_tensors(void) { return M_COUNT; }
+const char* cpb_mlpvae_tensor_name(int32_t i) { return (i >= 0 && i < M_COUNT) ? kMlpNames[i] : nullptr; }
+
+int32_t cpb_mlpvae_layout(const cpb_mlpvae_config* cfg, int64_t* offsets, int64_t* sizes, int32_t* shapes, int64_t* total) {
+    CPB_TRY(check_mlp_cfg(cfg));
+    MlpLayout L = make_mlp_layout(cfg);
+    for (int i = 0; i < M_COUNT; ++i) {
+        if (offsets) offsets[i] = L.off[i];
+        if (sizes) sizes[i] = L.size[i];
+        if (shapes) { shapes[i * 4] = L.shape[i][0]; shapes[i * 4 + 1] = L.shape[i][1]; shapes[i * 4 + 2] = 0; shapes[i * 4 + 3] = 0; }
+    }
+    if (total) *total = L.total;
+    return CPB_OK;
+}
+
+int64_t cpb_mlpvae_workspace_bytes(const cpb_mlpvae_config* cfg, int32_t mode) {
+    if (check_mlp_cfg(cfg) != CPB_OK || mode < 0 || mode > 2) return CPB_ERR_INVALID_ARGUMENT;
+    return make_mlp_plan(nullptr, 0, cfg, mode).bytes;
+}
+
+#define CPB_MLP_PLAN(mode)                                                                           \
+    CPB_TRY(check_mlp_cfg(cfg));                                                                     \
+    CPB_TRY(ensure_init());                                                                          \
+    CPB_REQUIRE(workspace != nullptr, "workspace is NULL");                                          \
+    MlpPlan pl = make_mlp_plan(workspace, workspace_bytes, cfg, mode);                               \
+    if (!pl.ok) {                                                                                    \
+        cpb::set_error("workspace too small: need %lld bytes, got %lld", (long long)pl.bytes, (long long)workspace_bytes); \
+        return CPB_ERR_WORKSPACE_TOO_SMALL;                                                          \
+    }                                                                                                \
+    MlpLayout L = make_mlp_layout(cfg);                                                              \
+    cudaStream_t s = (cudaStream_t)stream;
+
+int32_t cpb_mlpvae_encode(const cpb_mlpvae_config* cfg, const float* params, const void* source, float* mean, float* logvar,
+                          int32_t* flags, void* workspace, int64_t workspace_bytes, void* stream) {
+    CPB_MLP_PLAN(CPB_WS_ENCODE);
+    CPB_REQUIRE(params && source && mean, "mlp encode: NULL pointer");
+    CPB_TRY(mlp_encoder(pl, L, cfg, params, source, flags, s));
+    const size_t n = (size_t)pl.B * pl.z * sizeof(float);
+    CPB_CUDA(cudaMemcpyAsync(mean, pl.heads, n, cudaMemcpyDeviceToDevice, s));
+    if (logvar) CPB_CUDA(cudaMemcpyAsync(logvar, pl.heads + (long long)pl.B * pl.z, n, cudaMemcpyDeviceToDevice, s));
+    return CPB_OK;
+}
+
+int32_t cpb_mlpvae_decode(const cpb_mlpvae_config* cfg, const float* params, const float* z, float* reconstruction, void* workspace,
+                          int64_t workspace_bytes, void* stream) {
+    CPB_MLP_PLAN(CPB_WS_FORWARD);
+    CPB_REQUIRE(params && z && reconstruction, "mlp decode: NULL pointer");
+    CPB_TRY(mlp_decoder(pl, L, params, z, pl.logits, s));
+    return launch_sigmoid(pl.logits, reconstruction, (long long)pl.B * pl.OUT, s);
+}
+
+int32_t cpb_mlpvae_forward(const cpb_mlpvae_config* cfg, const float* params, const void* source, const void* target, const float* eps,
+                           float* losses, float* mean, float* logvar, float* z, float* reconstruction, int32_t* flags,
+                           void* workspace, int64_t workspace_bytes, void* stream) {
+    CPB_MLP_PLAN(CPB_WS_FORWARD);
+    CPB_REQUIRE(params && source && target && losses, "mlp forward: NULL pointer");
+    CPB_TRY(mlp_forward_loss(pl, L, cfg, params, source, target, eps, false, flags, s));
+    CPB_TRY(launch_finalize_losses(pl.frame_loss, pl.kl_rows, pl.B, cfg->base.loss_scale, losses, s));
+    const size_t n = (size_t)pl.B * pl.z * sizeof(float);
+    if (mean) CPB_CUDA(cudaMemcpyAsync(mean, pl.heads, n, cudaMemcpyDeviceToDevice, s));
+    if (logvar) CPB_CUDA(cudaMemcpyAsync(logvar, pl.heads + (long long)pl.B * pl.z, n, cudaMemcpyDeviceToDevice, s));
+    if (z) CPB_CUDA(cudaMemcpyAsync(z, pl.zbuf, n, cudaMemcpyDeviceToDevice, s));
+    if (reconstruction) CPB_TRY(launch_sigmoid(pl.logits, reconstruction, (long long)pl.B * pl.OUT, s));
+    return CPB_OK;
+}
+
+int32_t cpb_mlpvae_loss_grad(const cpb_mlpvae_config* cfg, const float* params, const void* source, const void* target, const float* eps,
+                             float* grads, float* losses, int32_t* flags, void* workspace, int64_t workspace_bytes, void* stream) {
+    CPB_MLP_PLAN(CPB_WS_TRAIN);
+    CPB_REQUIRE(params && source && target && grads && losses, "mlp loss_grad: NULL pointer");
+    CPB_TRY(mlp_forward_loss(pl, L, cfg, params, source, target, eps, true, flags, s));
+    CPB_TRY(launch_finalize_losses(pl.frame_loss, pl.kl_rows, pl.B, cfg->base.loss_scale, losses, s));
+    return mlp_backward(pl, L, cfg, params, eps, grads, s);
 }
 
 }  // extern "C"

@@ -24,7 +24,7 @@ from typing import Dict, Optional
 import numpy as np
 
 from .. import _lib
-from .._lib import CpbError, VaeConfig
+from .._lib import CpbError, MlpVaeConfig, VaeConfig
 
 
 # ----------------------------------------------------------------------------- loss selectors
@@ -92,6 +92,11 @@ class _Placeholder:
 class VAE:
     """Base class.  Geometry is the reference's only tested one: source [80,160,3], target [80,160,Ct]."""
 
+    # C entry points of the architecture (ConvVAE: cpb_vae_*, MlpVAE: cpb_mlpvae_*; identical argument lists)
+    _API = {"num_tensors": "cpb_vae_num_tensors", "tensor_name": "cpb_vae_tensor_name", "encode": "cpb_vae_encode",
+            "decode": "cpb_vae_decode", "forward": "cpb_vae_forward", "loss_grad": "cpb_vae_loss_grad"}
+    _HOST_STEP = True        # cpb_vae_train_step_host exists for this architecture
+
     def __init__(self, source_shape, target_shape, build_encoder_fn=None, build_decoder_fn=None,
                  z_dim=512, beta=1.0, learning_rate=1e-4, lr_decay=0.98, kl_tolerance=0.0,
                  model_dir=".", loss_fn=bce_loss, training=True, reuse=None, seed=None,
@@ -150,11 +155,11 @@ class VAE:
         if self._device.index is None:
             self._device = torch.device("cuda", torch.cuda.current_device())
         dev = self._device
-        n = lib.cpb_vae_num_tensors()
+        n = getattr(lib, self._API["num_tensors"])()
         offs = (C.c_int64 * n)(); sizes = (C.c_int64 * n)(); shapes = (C.c_int32 * (4 * n))()
         total = C.c_int64()
-        _lib.check(lib.cpb_vae_layout(self.target_shape[2], self.z_dim, offs, sizes, shapes, C.byref(total)), "cpb_vae_layout")
-        self._names = [lib.cpb_vae_tensor_name(i).decode() for i in range(n)]
+        self._query_layout(lib, offs, sizes, shapes, total)
+        self._names = [getattr(lib, self._API["tensor_name"])(i).decode() for i in range(n)]
         self._offsets = {self._names[i]: int(offs[i]) for i in range(n)}
         self._shapes = {self._names[i]: tuple(int(s) for s in shapes[4 * i:4 * i + 4] if s > 0) for i in range(n)}
         self._total = int(total.value)
@@ -178,6 +183,12 @@ class VAE:
         self.step_idx = 0
         if init_logging:
             self._init_logging()
+
+    def _query_layout(self, lib, offs, sizes, shapes, total):
+        _lib.check(lib.cpb_vae_layout(self.target_shape[2], self.z_dim, offs, sizes, shapes, C.byref(total)), "cpb_vae_layout")
+
+    def _workspace_need(self, batch, mode):
+        return self._libh.cpb_vae_workspace_bytes(batch, self.target_shape[2], self.z_dim, mode)
 
     def _initial_weights(self) -> Dict[str, np.ndarray]:
         rng = np.random.RandomState(self._seed if self._seed is not None else np.random.randint(0, 2 ** 31 - 1))
@@ -358,8 +369,8 @@ class VAE:
     # ------------------------------------------------------------------ plumbing
     def _workspace(self, batch, mode):
         key = mode
-        need = self._libh.cpb_vae_workspace_bytes(batch, self.target_shape[2], self.z_dim, mode)
-        _lib.check(need, "cpb_vae_workspace_bytes")
+        need = self._workspace_need(batch, mode)
+        _lib.check(need, "workspace_bytes")
         ws = self._ws.get(key)
         if ws is None or ws.numel() < need:
             self._ws[key] = None
@@ -424,7 +435,7 @@ class VAE:
         logvar = torch.empty_like(mean) if return_logvar else None
         ws = self._workspace(b, _lib.WS_ENCODE)
         cfg = self._config(b, self._frame_dtype(x))
-        self._call("cpb_vae_encode", C.byref(cfg), _lib.ptr(self.params), _lib.ptr(x), _lib.ptr(mean),
+        self._call(self._API["encode"], C.byref(cfg), _lib.ptr(self.params), _lib.ptr(x), _lib.ptr(mean),
                                              _lib.ptr(logvar), _lib.ptr(self._flags), _lib.ptr(ws), ws.numel(),
                                              self._stream())
         if check:
@@ -441,7 +452,7 @@ class VAE:
         out = torch.empty(b, 80 * 160 * self.target_shape[2], dtype=torch.float32, device=self._device)
         ws = self._workspace(b, _lib.WS_FORWARD)
         cfg = self._config(b)
-        self._call("cpb_vae_decode", C.byref(cfg), _lib.ptr(self.params), _lib.ptr(zt), _lib.ptr(out),
+        self._call(self._API["decode"], C.byref(cfg), _lib.ptr(self.params), _lib.ptr(zt), _lib.ptr(out),
                                              _lib.ptr(ws), ws.numel(), self._stream())
         return out.cpu().numpy()
 
@@ -475,7 +486,7 @@ class VAE:
             rec = torch.empty(b, 80 * 160 * self.target_shape[2], dtype=torch.float32, device=self._device)
         ws = self._workspace(b, _lib.WS_FORWARD)
         cfg = self._config(b, self._frame_dtype(x), self._frame_dtype(y), loss_scale)
-        self._call("cpb_vae_forward", C.byref(cfg), _lib.ptr(self.params), _lib.ptr(x), _lib.ptr(y),
+        self._call(self._API["forward"], C.byref(cfg), _lib.ptr(self.params), _lib.ptr(x), _lib.ptr(y),
                                               _lib.ptr(eps), _lib.ptr(losses), _lib.ptr(mean), _lib.ptr(logvar),
                                               _lib.ptr(z), _lib.ptr(rec), _lib.ptr(self._flags), _lib.ptr(ws),
                                               ws.numel(), self._stream())
@@ -503,7 +514,7 @@ class VAE:
         b = x.shape[0]
         ws = self._workspace(b, _lib.WS_TRAIN)
         cfg = self._config(b, self._frame_dtype(x), self._frame_dtype(y), loss_scale)
-        self._call("cpb_vae_loss_grad", C.byref(cfg), _lib.ptr(self.params), _lib.ptr(x), _lib.ptr(y),
+        self._call(self._API["loss_grad"], C.byref(cfg), _lib.ptr(self.params), _lib.ptr(x), _lib.ptr(y),
                                                 _lib.ptr(eps), _lib.ptr(self.grads), _lib.ptr(self._losses),
                                                 _lib.ptr(self._flags), _lib.ptr(ws), ws.numel(),
                                                 self._stream())
@@ -542,7 +553,7 @@ class VAE:
             raise CpbError("this VAE was built with training=False")
         torch = self._torch
         world, _ = self._world()
-        if world > 1 or isinstance(source, torch.Tensor):
+        if world > 1 or isinstance(source, torch.Tensor) or not self._HOST_STEP:
             x = self._to_device_frames(source, 3)
             y = x if target is source else self._to_device_frames(target, self.target_shape[2])
             e = None if eps is None else torch.as_tensor(np.asarray(eps, np.float32), device=self._device)
@@ -752,8 +763,33 @@ class ConvVAE(VAE):
 
 
 class MlpVAE(VAE):
-    """The reference's dense VAE (vae/models.py:271-299).  Out of the hot-path scope of this build
-    (SURVEY.md section 8f, item 4): constructing it raises instead of silently running something else."""
+    """The reference's dense VAE (vae/models.py:271-299): flatten -> dense(encoder_sizes, relu) -> mean / logstd_sqare ->
+    sample -> dense(decoder_sizes, relu) -> dense(prod(target_shape)) = logits.  Same surface as ConvVAE; the seven
+    dense layers run on the fp32 SIMT kernels of the library (cpb_mlpvae_* entry points)."""
 
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError("MlpVAE is outside the B200 hot path built so far (ConvVAE only)")
+    _API = {"num_tensors": "cpb_mlpvae_num_tensors", "tensor_name": "cpb_mlpvae_tensor_name", "encode": "cpb_mlpvae_encode",
+            "decode": "cpb_mlpvae_decode", "forward": "cpb_mlpvae_forward", "loss_grad": "cpb_mlpvae_loss_grad"}
+    _HOST_STEP = False
+
+    def __init__(self, source_shape, target_shape=None, encoder_sizes=(512, 256), decoder_sizes=(256, 512), **kwargs):
+        target_shape = source_shape if target_shape is None else target_shape
+        if len(encoder_sizes) != 2 or len(decoder_sizes) != 2:
+            raise ValueError("MlpVAE is built for two hidden layers per side (the reference's defaults (512,256)/(256,512))")
+        self.encoder_sizes = tuple(int(v) for v in encoder_sizes)
+        self.decoder_sizes = tuple(int(v) for v in decoder_sizes)
+        super().__init__(source_shape, target_shape, None, None, **kwargs)
+        self.encoded_shape = (self.encoder_sizes[-1],)
+
+    def _mlp_config(self, batch, source_dtype=_lib.FRAME_F32, target_dtype=_lib.FRAME_F32, loss_scale=1.0):
+        base = VAE._config(self, batch, source_dtype, target_dtype, loss_scale)
+        return MlpVaeConfig(base, self.encoder_sizes[0], self.encoder_sizes[1], self.decoder_sizes[0], self.decoder_sizes[1])
+
+    _config = _mlp_config
+
+    def _query_layout(self, lib, offs, sizes, shapes, total):
+        cfg = self._mlp_config(1)
+        _lib.check(lib.cpb_mlpvae_layout(C.byref(cfg), offs, sizes, shapes, C.byref(total)), "cpb_mlpvae_layout")
+
+    def _workspace_need(self, batch, mode):
+        cfg = self._mlp_config(batch)
+        return self._libh.cpb_mlpvae_workspace_bytes(C.byref(cfg), mode)

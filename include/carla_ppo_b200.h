@@ -144,6 +144,35 @@ int32_t cpb_vae_train_step_host(const cpb_vae_config* cfg, float* params, float*
                                 void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * MlpVAE (vae/models.py:271-299): flatten(38400) -> dense enc1 relu -> dense enc2 relu -> mean / logstd_sqare heads ->
+ * sample -> dense dec1 relu -> dense dec2 relu -> dense 12800*Ct (logits).  Same conventions as the ConvVAE entry points
+ * above (flat parameter buffer described by cpb_mlpvae_layout, caller-owned workspace, same loss / flag semantics); the
+ * optimiser is cpb_adam_apply(_guarded) on the flat buffers.  14 variables: encoder/dense{,_1}, mean, logstd_sqare,
+ * decoder/dense{,_1,_2}, each {kernel [in,out], bias}.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    cpb_vae_config base;               /* batch, target_channels, z_dim, loss, dtypes, beta, kl_tolerance, loss_scale */
+    int32_t enc1, enc2;                /* encoder_sizes (512, 256)   (vae/models.py:277) */
+    int32_t dec1, dec2;                /* decoder_sizes (256, 512)   (vae/models.py:278) */
+} cpb_mlpvae_config;
+
+int32_t     cpb_mlpvae_num_tensors(void);
+const char* cpb_mlpvae_tensor_name(int32_t index);
+int32_t cpb_mlpvae_layout(const cpb_mlpvae_config* cfg, int64_t* offsets, int64_t* sizes, int32_t* shapes /* 4 per tensor */,
+                          int64_t* total_floats);
+int64_t cpb_mlpvae_workspace_bytes(const cpb_mlpvae_config* cfg, int32_t mode);
+int32_t cpb_mlpvae_encode(const cpb_mlpvae_config* cfg, const float* params, const void* source, float* mean, float* logvar,
+                          int32_t* flags, void* workspace, int64_t workspace_bytes, void* stream);
+int32_t cpb_mlpvae_decode(const cpb_mlpvae_config* cfg, const float* params, const float* z, float* reconstruction,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+int32_t cpb_mlpvae_forward(const cpb_mlpvae_config* cfg, const float* params, const void* source, const void* target,
+                           const float* eps, float* losses, float* mean, float* logvar, float* z, float* reconstruction,
+                           int32_t* flags, void* workspace, int64_t workspace_bytes, void* stream);
+int32_t cpb_mlpvae_loss_grad(const cpb_mlpvae_config* cfg, const float* params, const void* source, const void* target,
+                             const float* eps, float* grads, float* losses, int32_t* flags, void* workspace,
+                             int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * PPO (ppo.py, utils.py:45-50, train.py:171-207)
  * ---------------------------------------------------------------------------------------- */
 typedef struct {

@@ -228,3 +228,35 @@ class TorchPPOLearner:
                                    self.epsilon, self.value_scale, self.entropy_scale)
                 loss.backward()
                 self.opt.step()
+
+
+# ----------------------------------------------------------------------------- MlpVAE (independent autograd derivation)
+def mlp_vae_loss_and_grads(params, x, y, eps, loss_type="mse", beta=1.0, kl_tolerance=0.0, dtype=torch.float64):
+    """vae/models.py:271-299 with stock torch ops + autograd; the check of vae_oracle.mlp_loss_and_grads' hand-written backward."""
+    p = vae_params_to_torch(params, dtype)
+    xt, yt, et = _t(x, dtype), _t(y, dtype), _t(eps, dtype)
+    b = xt.shape[0]
+    h = F.relu(xt.reshape(b, -1) @ p["encoder/dense/kernel"] + p["encoder/dense/bias"])
+    h = F.relu(h @ p["encoder/dense_1/kernel"] + p["encoder/dense_1/bias"])
+    mean = h @ p["mean/kernel"] + p["mean/bias"]
+    logvar = h @ p["logstd_sqare/kernel"] + p["logstd_sqare/bias"]
+    z = mean + et * torch.exp(0.5 * logvar)
+    g = F.relu(z @ p["decoder/dense/kernel"] + p["decoder/dense/bias"])
+    g = F.relu(g @ p["decoder/dense_1/kernel"] + p["decoder/dense_1/bias"])
+    lf = g @ p["decoder/dense_2/kernel"] + p["decoder/dense_2/bias"]
+    yf = yt.reshape(b, -1)
+    if loss_type == "mse":
+        elem = (yf - torch.sigmoid(lf)) ** 2
+    elif loss_type == "bce":
+        elem = F.binary_cross_entropy_with_logits(lf, yf, reduction="none")
+    else:
+        sg = torch.sigmoid(lf)
+        elem = -(yf * torch.log(1e-10 + sg) + (1 - yf) * torch.log(1e-10 + 1 - sg))
+    recon = elem.sum(dim=1).mean()
+    kl_rows = -0.5 * torch.sum(1.0 + logvar - mean * mean - torch.exp(logvar), dim=1)
+    if kl_tolerance > 0:
+        kl_rows = torch.maximum(kl_rows, torch.full_like(kl_rows, kl_tolerance * mean.shape[1]))
+    kl = kl_rows.mean()
+    (recon + beta * kl).backward()
+    return dict(mean=mean.detach().numpy(), logvar=logvar.detach().numpy(), logits=lf.detach().numpy(), recon=float(recon.detach()),
+                kl=float(kl.detach()), grads={k: v.grad.numpy() for k, v in p.items()})

@@ -333,3 +333,87 @@ def train_step(params, state, x, y, eps, lr=1e-4, loss_type="mse", beta=1.0, kl_
     out = loss_and_grads(params, x, y, eps, loss_type, beta, kl_tolerance, True, dtype)
     adam_apply(params, out["grads"], state, lr)
     return out["recon"], out["kl"]
+
+
+# ----------------------------------------------------------------------------- MlpVAE (vae/models.py:271-299)
+def mlp_param_shapes(source_shape=(80, 160, 3), target_channels=3, z_dim=Z_DIM_DEFAULT, encoder_sizes=(512, 256), decoder_sizes=(256, 512)):
+    """tf.layers.dense variables in creation order: encoder/dense, encoder/dense_1, mean, logstd_sqare, decoder/dense,
+    decoder/dense_1, decoder/dense_2 (build_mlp, vae/models.py:283-296)."""
+    n_in = int(np.prod(source_shape))
+    n_out = source_shape[0] * source_shape[1] * target_channels
+    s = OrderedDict()
+    s["encoder/dense/kernel"] = (n_in, encoder_sizes[0]);                  s["encoder/dense/bias"] = (encoder_sizes[0],)
+    s["encoder/dense_1/kernel"] = (encoder_sizes[0], encoder_sizes[1]);    s["encoder/dense_1/bias"] = (encoder_sizes[1],)
+    s["mean/kernel"] = (encoder_sizes[1], z_dim);                          s["mean/bias"] = (z_dim,)
+    s["logstd_sqare/kernel"] = (encoder_sizes[1], z_dim);                  s["logstd_sqare/bias"] = (z_dim,)
+    s["decoder/dense/kernel"] = (z_dim, decoder_sizes[0]);                 s["decoder/dense/bias"] = (decoder_sizes[0],)
+    s["decoder/dense_1/kernel"] = (decoder_sizes[0], decoder_sizes[1]);    s["decoder/dense_1/bias"] = (decoder_sizes[1],)
+    s["decoder/dense_2/kernel"] = (decoder_sizes[1], n_out);               s["decoder/dense_2/bias"] = (n_out,)
+    return s
+
+
+def mlp_glorot_init(seed=0, dtype=np.float32, **kw):
+    rng = np.random.RandomState(seed)
+    out = OrderedDict()
+    for name, shape in mlp_param_shapes(**kw).items():
+        if name.endswith("bias"):
+            out[name] = np.zeros(shape, dtype)
+        else:
+            limit = np.sqrt(6.0 / (shape[0] + shape[1]))
+            out[name] = rng.uniform(-limit, limit, size=shape).astype(dtype)
+    return out
+
+
+def mlp_loss_and_grads(params, x, y, eps, loss_type="mse", beta=1.0, kl_tolerance=0.0, want_grads=True, dtype=np.float64):
+    """Forward + loss (+ hand-derived gradients) of the MlpVAE graph; x [B,H,W,3], y [B,H,W,C_t], eps [B,z]."""
+    p = {k: np.asarray(v, dtype) for k, v in params.items()}
+    x = np.asarray(x, dtype); y = np.asarray(y, dtype); eps = np.asarray(eps, dtype)
+    verify_range(x); verify_range(y)
+    b = x.shape[0]
+    xf = x.reshape(b, -1); yf = y.reshape(b, -1)
+    h1 = np.maximum(xf @ p["encoder/dense/kernel"] + p["encoder/dense/bias"], 0.0)
+    h2 = np.maximum(h1 @ p["encoder/dense_1/kernel"] + p["encoder/dense_1/bias"], 0.0)
+    mean = h2 @ p["mean/kernel"] + p["mean/bias"]
+    logvar = h2 @ p["logstd_sqare/kernel"] + p["logstd_sqare/bias"]
+    std = np.exp(0.5 * logvar)
+    z = mean + eps * std
+    g1 = np.maximum(z @ p["decoder/dense/kernel"] + p["decoder/dense/bias"], 0.0)
+    g2 = np.maximum(g1 @ p["decoder/dense_1/kernel"] + p["decoder/dense_1/bias"], 0.0)
+    logits = g2 @ p["decoder/dense_2/kernel"] + p["decoder/dense_2/bias"]
+    elem, dlogit = recon_elem(loss_type, yf, logits)
+    recon = elem.sum(axis=1).mean()
+    kl_rows = -0.5 * np.sum(1.0 + logvar - mean * mean - np.exp(logvar), axis=1)
+    kl_active = np.ones(b, dtype=bool)
+    if kl_tolerance > 0:
+        floor = kl_tolerance * mean.shape[1]
+        kl_active = kl_rows >= floor
+        kl_rows = np.maximum(kl_rows, floor)
+    kl = kl_rows.mean()
+    out = dict(mean=mean, logvar=logvar, z=z, logits=logits, recon=recon, kl=kl, loss=recon + beta * kl)
+    if not want_grads:
+        return out
+    g = {}
+    gl = dlogit / b
+    g["decoder/dense_2/kernel"] = g2.T @ gl; g["decoder/dense_2/bias"] = gl.sum(axis=0)
+    d = (gl @ p["decoder/dense_2/kernel"].T) * (g2 > 0)
+    g["decoder/dense_1/kernel"] = g1.T @ d; g["decoder/dense_1/bias"] = d.sum(axis=0)
+    d = (d @ p["decoder/dense_1/kernel"].T) * (g1 > 0)
+    g["decoder/dense/kernel"] = z.T @ d; g["decoder/dense/bias"] = d.sum(axis=0)
+    gz = d @ p["decoder/dense/kernel"].T
+    klmask = kl_active[:, None].astype(dtype)
+    gmean = gz + (beta / b) * mean * klmask
+    glogvar = gz * (0.5 * eps * std) + (beta / b) * 0.5 * (np.exp(logvar) - 1.0) * klmask
+    g["mean/kernel"] = h2.T @ gmean; g["mean/bias"] = gmean.sum(axis=0)
+    g["logstd_sqare/kernel"] = h2.T @ glogvar; g["logstd_sqare/bias"] = glogvar.sum(axis=0)
+    d = (gmean @ p["mean/kernel"].T + glogvar @ p["logstd_sqare/kernel"].T) * (h2 > 0)
+    g["encoder/dense_1/kernel"] = h1.T @ d; g["encoder/dense_1/bias"] = d.sum(axis=0)
+    d = (d @ p["encoder/dense_1/kernel"].T) * (h1 > 0)
+    g["encoder/dense/kernel"] = xf.T @ d; g["encoder/dense/bias"] = d.sum(axis=0)
+    out["grads"] = g
+    return out
+
+
+def mlp_train_step(params, state, x, y, eps, lr=1e-4, loss_type="mse", beta=1.0, kl_tolerance=0.0, dtype=np.float64):
+    out = mlp_loss_and_grads(params, x, y, eps, loss_type, beta, kl_tolerance, True, dtype)
+    adam_apply(params, out["grads"], state, lr)
+    return out["recon"], out["kl"]

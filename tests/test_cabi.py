@@ -117,8 +117,10 @@ def test_classes_fail_loudly_without_cuda(tmp_path):
         vae.init_session()                       # no CPU fallback
     with pytest.raises(CpbError):
         vae.encode(np.zeros((1, 80, 160, 3), np.float32))
-    with pytest.raises(NotImplementedError):
-        MlpVAE((80, 160, 3))
+    mlp = MlpVAE((80, 160, 3), z_dim=64, model_dir=str(tmp_path / "mlp"))     # reference vae/models.py:271-299
+    assert mlp.encoder_sizes == (512, 256) and mlp.decoder_sizes == (256, 512)
+    with pytest.raises(CpbError):
+        mlp.init_session()                       # no CPU fallback either
     with pytest.raises(ValueError):
         ConvVAE((64, 64, 3), model_dir=str(tmp_path / "w"))
     x = np.array([0.3, -1.2]); y = np.array([1.0, 0.0])

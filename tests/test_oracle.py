@@ -254,3 +254,20 @@ def test_tf_bundle_crc_and_entries_pinned_to_a_shipped_checkpoint(tmp_path):
     a, b = tb.BundleReader(prefix), tb.BundleReader(str(tmp_path / "x"))
     for k in small:
         assert a.entries[k][:2] == b.entries[k][:2] and a.entries[k][3] == b.entries[k][3]
+
+
+def test_mlp_vae_backward_matches_autograd():
+    """MlpVAE (vae/models.py:271-299): hand-derived backward of the oracle vs torch autograd, all three losses."""
+    from oracle import vae_oracle as vo, torch_ref as tr
+    kw = dict(encoder_sizes=(64, 32), decoder_sizes=(32, 64))
+    p = vo.mlp_glorot_init(3, **kw)
+    shapes = vo.mlp_param_shapes()
+    assert shapes["encoder/dense/kernel"] == (38400, 512) and shapes["decoder/dense_2/kernel"] == (512, 38400) and len(shapes) == 14
+    rs = np.random.RandomState(0)
+    x = rs.rand(3, 80, 160, 3).astype(np.float32); eps = rs.randn(3, 64)
+    for loss, beta, tol in (("mse", 1.0, 0.0), ("bce", 2.0, 0.0), ("bce_v2", 1.0, 0.3)):
+        a = vo.mlp_loss_and_grads(p, x, x, eps, loss, beta, tol)
+        b = tr.mlp_vae_loss_and_grads(p, x, x, eps, loss, beta, tol)
+        assert abs(a["recon"] - b["recon"]) < 1e-9 * abs(b["recon"]) and abs(a["kl"] - b["kl"]) < 1e-9 * max(abs(b["kl"]), 1)
+        for k in a["grads"]:
+            assert rel_l2(a["grads"][k], b["grads"][k]) < 1e-10, (loss, k)

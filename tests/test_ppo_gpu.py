@@ -211,3 +211,34 @@ def test_update_old_policy_and_zero_epoch_learn(tmp_path):
     assert out.shape == (0, 5)
     assert all(np.array_equal(m.get_old_weights()[k], pol[k]) for k in pol)
     assert all(np.array_equal(m.get_weights()[k], pol[k]) for k in pol)
+
+
+def test_persistent_learn_kernel_matches_launch_per_kernel_path(tmp_path):
+    """CPB_PPO_PERSISTENT=1 (one cooperative kernel for all minibatch steps) vs the default launch-per-kernel learn():
+    same parameters to fp32 round-off (the per-CTA loss partials are summed in a different order)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    snippet = r"""
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import test_ppo_gpu as t
+from helpers import shipped_ppo
+from pathlib import Path
+pol, z = shipped_ppo("policy")
+m = t.make_ppo(Path(%r), pol, pol)
+m.set_weights(pol, pol, {k: z["adam_m/" + k] for k in pol}, {k: z["adam_v/" + k] for k in pol}, (float(z["beta1_power"]), float(z["beta2_power"])))
+s, a, r, v, d, perms = t._baseline_config3(2048, 2)
+m.learn(s, a, v, r, d, 0.3, num_epochs=2, batch_size=200, perms=perms)       # ragged last minibatch (2048 = 10 x 200 + 48)
+np.savez(%r, **m.get_weights())
+"""
+    outs = []
+    for flag in ("0", "1"):
+        out = str(tmp_path / ("w%s.npz" % flag))
+        code = snippet % (root, os.path.join(root, "tests"), str(tmp_path / ("m" + flag)), out)
+        res = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CPB_PPO_PERSISTENT=flag), capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0, res.stderr[-2000:]
+        outs.append(dict(np.load(out)))
+    for k in outs[0]:
+        assert rel_l2(outs[1][k], outs[0][k]) < 1e-6, (k, rel_l2(outs[1][k], outs[0][k]))
