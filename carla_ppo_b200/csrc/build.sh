@@ -4,7 +4,7 @@
 set -e
 cd "$(dirname "$0")"
 OUT=../libcarla_ppo_b200.so
-SRCS="vae_api.cu tapgemm.cu tc_tapgemm.cu tc2_tapgemm.cu tc2_wgrad.cu tc_wgrad.cu wgrad.cu elementwise.cu edge.cu ppo.cu"
+SRCS="vae_api.cu tapgemm.cu tc_tapgemm.cu tc2_tapgemm.cu tc2_wgrad.cu tc3_wgrad.cu tc_wgrad.cu wgrad.cu elementwise.cu edge.cu ppo.cu"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC"
 mkdir -p ../build
 OBJS=""

@@ -42,7 +42,7 @@ PpoLayout make_ppo_layout(const cpb_ppo_config* c) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// small tile GEMM: C[M,N] (+)= A'[M,K] * B'[K,N], 32x32 tile, 64 threads, 4x4 per thread
+// small tile GEMM: C[M,N] (+)= A'[M,K] * B'[K,N], 32x32 tile, 128 threads, 2x4 per thread
 // ---------------------------------------------------------------------------------------------
 constexpr int TS = 32;   // tile edge
 constexpr int TK = 64;   // reduction chunk (one global round trip per chunk: keep the chunk count low)
@@ -80,29 +80,33 @@ struct GemmBatch {
     GemmJob job[6];       // independent GEMMs of one launch (blockIdx.z); all with the same gather mode
 };
 
-// One 32x32 output tile of job J by a GROUP of 64 threads (tid = 0..63).  `sync()` is the group's barrier: __syncthreads in
-// the stand-alone kernel (one group per CTA), a named barrier in the persistent learn() kernel (four groups per CTA).
-// As / Bs: the group's double-buffered operand tiles [2][TK][TS + 4].
+// One 32x32 output tile of job J by a GROUP of kTileThreads = 128 threads (tid = 0..127), 2x4 outputs per thread.  `sync()` is
+// the group's barrier: __syncthreads in the stand-alone kernel (one group per CTA), a named barrier in the persistent learn()
+// kernel (two groups per CTA).  As / Bs: the group's double-buffered operand tiles [2][TK][TS + 4].
+// (Round 1 used 64 threads with 4x4 outputs: 1024 dependent-issue FMAs per thread and 64-wide chunk made every K = 500 tile
+// a ~12 us chain; with 128 threads the per-chunk FMA chain halves and twice the warps hide the chunk's global round trip.)
+constexpr int kTileThreads = 128;
+
 template <int GATHER, typename Sync>
 __device__ __forceinline__ void gemm_tile(const GemmJob& J, int m0, int n0, bool first_m_tile, int tid,
                                           float (*As)[TK][TS + 4], float (*Bs)[TK][TS + 4], Sync sync) {
-    const int tx = tid & 7, ty = tid >> 3;      // 8 x 8 threads, 4x4 outputs each
-    float acc[4][4];
+    const int tx = tid & 7, ty = tid >> 3;      // 8 x 16 threads, 2 rows x 4 columns each
+    float acc[2][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     float csum = 0.f;                            // column-sum lane (threads 0..31 own column n0+tid)
     const bool do_colsum = J.colsum != nullptr && first_m_tile;
     const bool a_ofast = J.a.so <= J.a.sr, b_ofast = J.b.so <= J.b.sr;
 
-    constexpr int EPT = TS * TK / 64;           // elements per thread per operand and chunk
+    constexpr int EPT = TS * TK / kTileThreads;  // elements per thread per operand and chunk
     float ra[EPT], rb[EPT];
     auto fetch_chunk = [&](int r0) {
         // TS*TK elements per operand; the faster-varying thread index follows the contiguous memory direction
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
-            const int f = tid + e * 64;
+            const int f = tid + e * kTileThreads;
             int o, r;
             if (a_ofast) { o = f & 31; r = f >> 5; } else { r = f & (TK - 1); o = f / TK; }
             ra[e] = (m0 + o < J.M && r0 + r < J.R) ? __ldcg(J.a.p + a_offset<GATHER>(J.a, m0 + o, r0 + r)) : 0.f;
@@ -115,7 +119,7 @@ __device__ __forceinline__ void gemm_tile(const GemmJob& J, int m0, int n0, bool
     for (int r0 = 0; r0 < J.R; r0 += TK, buf ^= 1) {
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
-            const int f = tid + e * 64;
+            const int f = tid + e * kTileThreads;
             int o, r;
             if (a_ofast) { o = f & 31; r = f >> 5; } else { r = f & (TK - 1); o = f / TK; }
             As[buf][r][o] = ra[e];
@@ -126,12 +130,12 @@ __device__ __forceinline__ void gemm_tile(const GemmJob& J, int m0, int n0, bool
         if (r0 + TK < J.R) fetch_chunk(r0 + TK);
 #pragma unroll
         for (int k = 0; k < TK; ++k) {
-            const float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+            const float2 a = *reinterpret_cast<const float2*>(&As[buf][k][ty * 2]);
             const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
-            const float av[4] = {a.x, a.y, a.z, a.w};
+            const float av[2] = {a.x, a.y};
             const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 2; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
@@ -141,8 +145,8 @@ __device__ __forceinline__ void gemm_tile(const GemmJob& J, int m0, int n0, bool
         }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = m0 + ty * 4 + i;
+    for (int i = 0; i < 2; ++i) {
+        const int m = m0 + ty * 2 + i;
         if (m >= J.M) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -159,7 +163,7 @@ __device__ __forceinline__ void gemm_tile(const GemmJob& J, int m0, int n0, bool
 }
 
 template <int GATHER>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(kTileThreads)
 small_gemm_kernel(const __grid_constant__ GemmBatch batch) {
     const GemmJob& J = batch.job[blockIdx.z];
     const int m0 = blockIdx.x * TS, n0 = blockIdx.y * TS;
@@ -179,9 +183,9 @@ int32_t launch_small_gemm(const GemmBatch& b, int njobs, cudaStream_t s) {
     if (maxM == 0 || maxN == 0) return CPB_OK;
     dim3 grid(cdiv(maxM, TS), cdiv(maxN, TS), njobs);
     const int gather = b.job[0].a.gather == nullptr ? 0 : (b.job[0].a.gather_on_o ? 1 : 2);   // same for all jobs of a batch
-    if (gather == 0) small_gemm_kernel<0><<<grid, 64, 0, s>>>(b);
-    else if (gather == 1) small_gemm_kernel<1><<<grid, 64, 0, s>>>(b);
-    else small_gemm_kernel<2><<<grid, 64, 0, s>>>(b);
+    if (gather == 0) small_gemm_kernel<0><<<grid, kTileThreads, 0, s>>>(b);
+    else if (gather == 1) small_gemm_kernel<1><<<grid, kTileThreads, 0, s>>>(b);
+    else small_gemm_kernel<2><<<grid, kTileThreads, 0, s>>>(b);
     CPB_LAUNCHED();
     return CPB_OK;
 }
@@ -627,7 +631,7 @@ int32_t run_loss_grad(const cpb_ppo_config* c, const PpoLayout& L, const PpoPlan
 // The driver's whole update block as ONE persistent cooperative kernel (train.py:171-207 after GAE / theta_old):
 // num_epochs x ceil(T / batch) minibatch steps, each = forward (2 trunks x 2 layers) -> head + loss -> backward ->
 // TF-Adam, with grid-wide barriers between the dependent phases instead of ~9 kernel launches per minibatch (round 1:
-// ~330 launches of 5-30 us kernels, 5.3 ms per learn()).  One CTA per SM, 4 independent groups of 64 threads per CTA;
+// ~330 launches of 5-30 us kernels, 5.3 ms per learn()).  One CTA per SM, 2 independent groups of 128 threads per CTA;
 // a phase's 32x32 output tiles are dealt round-robin to the 4 x gridDim groups; the arithmetic per tile is the
 // stand-alone small_gemm_kernel's (same gemm_tile), so the results are those of the launch-per-kernel path up to the
 // order in which the per-CTA loss partials are summed.
@@ -644,15 +648,15 @@ struct LearnArgs {
     int T, batch_size, num_epochs, nmb;
 };
 
-constexpr int kGroupsPerCta = 4;
-constexpr int kLearnThreads = kGroupsPerCta * 64;
+constexpr int kGroupsPerCta = 2;
+constexpr int kLearnThreads = kGroupsPerCta * kTileThreads;
 constexpr size_t kLearnSmem = (size_t)kGroupsPerCta * 2 * 2 * TK * (TS + 4) * sizeof(float);
 
 __device__ __forceinline__ int tiles_of(int n) { return (n + TS - 1) / TS; }
 
 template <int GATHER>
 __device__ __forceinline__ void run_phase(const GemmJob* jobs, int njobs, float* smem, int gid, int ngroups) {
-    const int group = threadIdx.x >> 6, gtid = threadIdx.x & 63;
+    const int group = threadIdx.x / kTileThreads, gtid = threadIdx.x % kTileThreads;
     float (*As)[TK][TS + 4] = reinterpret_cast<float (*)[TK][TS + 4]>(smem + (size_t)group * 2 * 2 * TK * (TS + 4));
     float (*Bs)[TK][TS + 4] = As + 2;
     int total = 0;
@@ -667,7 +671,7 @@ __device__ __forceinline__ void run_phase(const GemmJob* jobs, int njobs, float*
         const int mt = tiles_of(jobs[j].M);
         const int mi = r % mt, ni = r / mt;
         gemm_tile<GATHER>(jobs[j], mi * TS, ni * TS, mi == 0, gtid, As, Bs,
-                          [group] { asm volatile("bar.sync %0, 64;" ::"r"(group + 1) : "memory"); });
+                          [group] { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); });
     }
 }
 
@@ -683,7 +687,7 @@ ppo_learn_persistent_kernel(const __grid_constant__ LearnArgs a) {
     const PpoPlan& pl = a.pl;
     const int S = c.state_dim, H1 = c.hidden1, H2 = c.hidden2, A = c.num_actions;
     const int ngroups = gridDim.x * kGroupsPerCta;
-    const int gid = blockIdx.x * kGroupsPerCta + (threadIdx.x >> 6);
+    const int gid = blockIdx.x * kGroupsPerCta + threadIdx.x / kTileThreads;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* params = a.params;
     float* grads = a.grads;

@@ -75,4 +75,11 @@ void tc2_wgrad_plan(const WgradParams& w, int& bw, int& bh, int& bn, long long& 
 int tc2_wgrad_pick_splits(int I, int J, long long nboxes);
 int32_t launch_tc2_wgrad(const WgradParams& w, cudaStream_t stream);      // w.splits from tc2_wgrad_pick_splits; w.tc_variant & 1: descriptor probe
 
+// ---- weight gradient with the A operand in tensor memory (tc3_wgrad.cu), J = 32 / 64
+int32_t tc3_wgrad_init();
+bool tc3_wgrad_supported(const WgradParams& w);     // enabled (CPB_TC3_WGRAD=1) and the shape fits
+bool tc3_wgrad_available(const WgradParams& w);     // the shape fits (unit tests go through cpb_debug_tc_wgrad)
+long long tc3_wgrad_boxes(const WgradParams& w);                          // k-blocks (boxes of 32 positions) of the whole reduction
+int32_t launch_tc3_wgrad(const WgradParams& w, cudaStream_t stream);      // w.splits <= 148 / tiles, <= boxes
+
 }  // namespace cpb

@@ -32,7 +32,14 @@ struct TcWgCfg {
     static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
     static constexpr int STAGES = (STAGE_BYTES * 4 <= 200 * 1024) ? 4 : 3;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
-    static constexpr int TMEM_COLS = BN == 128 ? 512 : (BN == 64 ? 256 : 128);
+    // MERGED (BN <= 64): [main | cross] (+)= a_hi x [b_hi | b_lo] as ONE N = 2*BN MMA + cross += a_lo x b_hi, i.e. 8 instead of 12
+    // instructions per k-block (every M = 128 tcgen05.mma costs ~95 clk however narrow N is); the cross terms then reset per
+    // chunk with the main ones and are drained with them.  Measured: deconv3.wgrad 3.27 -> 2.94 ms, conv2.wgrad 1.85 -> 1.70 ms.
+    // At BN = 128 the doubled per-chunk drain (done by the A-loader warps, which are the LSU-bound part of this kernel) costs
+    // more than the saved instruction: 0.96 -> 2.30 ms -- so BN = 128 keeps three N = 128 MMAs and ONE cross accumulator that
+    // lives for the whole reduction.
+    static constexpr bool MERGED = BN <= 64;
+    static constexpr int TMEM_COLS = MERGED ? 4 * BN : (BN == 128 ? 512 : (BN == 64 ? 256 : 128));
 };
 
 constexpr int kWgLoaderWarps = 8;                         // warps 0-7: A (big) loaders, accumulator drain, partial store
@@ -106,7 +113,7 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
         // ================================ MMA issuer ================================
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
-            const uint32_t d_cross = tmem_base + (uint32_t)(2 * BN);
+            const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t stage = smem_base + s * STAGE_BYTES;
@@ -118,18 +125,30 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
                 const uint64_t a_hi = make_desc(stage);
                 const uint64_t a_lo = make_desc(stage + A_TILE_BYTES);
                 const uint64_t b_hi = make_desc(stage + 2 * A_TILE_BYTES);
-                const uint64_t b_lo = make_desc(stage + 2 * A_TILE_BYTES + B_TILE_BYTES);
-                const uint32_t d_main = tmem_base + (uint32_t)((chunk & 1) * BN);
+                if constexpr (Cfg::MERGED) {
+                    const uint32_t d_main = tmem_base + (uint32_t)((chunk & 1) * 2 * BN);
+                    const uint32_t d_cross = d_main + (uint32_t)BN;
 #pragma unroll
-                for (int ks = 0; ks < TBK / 8; ++ks) {
-                    const uint64_t adv = (uint64_t)(ks * 2);          // 32 bytes per k-step (K-major)
-                    umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, ((kb % CHUNK_KB) | ks) != 0 ? 1u : 0u);
-                    umma_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
-                    umma_tf32(d_cross, a_hi + adv, b_lo + adv, idesc, 1u);
+                    for (int ks = 0; ks < TBK / 8; ++ks) {
+                        const uint64_t adv = (uint64_t)(ks * 2);          // 32 bytes per k-step (K-major)
+                        umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc2, ((kb % CHUNK_KB) | ks) != 0 ? 1u : 0u);
+                        umma_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, 1u);
+                    }
+                } else {
+                    const uint64_t b_lo = make_desc(stage + 2 * A_TILE_BYTES + B_TILE_BYTES);
+                    const uint32_t d_main = tmem_base + (uint32_t)((chunk & 1) * BN);
+                    const uint32_t d_cross = tmem_base + (uint32_t)(2 * BN);
+#pragma unroll
+                    for (int ks = 0; ks < TBK / 8; ++ks) {
+                        const uint64_t adv = (uint64_t)(ks * 2);
+                        umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, ((kb % CHUNK_KB) | ks) != 0 ? 1u : 0u);
+                        umma_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, (kb | ks) != 0 ? 1u : 0u);
+                        umma_tf32(d_cross, a_hi + adv, b_lo + adv, idesc, 1u);
+                    }
                 }
                 umma_commit(&empty_bar[s]);
                 if (kb % CHUNK_KB == CHUNK_KB - 1 || kb == nkb - 1) umma_commit(&chunk_bar[chunk & 1]);
-                if (kb == nkb - 1) umma_commit(&done_bar);
+                if (!Cfg::MERGED && kb == nkb - 1) umma_commit(&done_bar);
             }
         }
         __syncwarp();
@@ -272,7 +291,12 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
             const int b = drained & 1;
             mbar_wait(&chunk_bar[b], (uint32_t)((drained >> 1) & 1));
             tc_fence_after();
-            drain_cols(tmem_lane + (uint32_t)(b * BN));
+            if constexpr (Cfg::MERGED) {
+                drain_cols(tmem_lane + (uint32_t)(b * 2 * BN));            // main term of the chunk
+                drain_cols(tmem_lane + (uint32_t)(b * 2 * BN + BN));       // its cross terms
+            } else {
+                drain_cols(tmem_lane + (uint32_t)(b * BN));
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&drained_bar[b]);
@@ -304,11 +328,11 @@ tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
             if (kb + 1 < nkb) step(kb + 1, xa1);
         }
 
-        if (nkb > 0) {
-            while (drained < nchunks) drain_one();
+        while (drained < nchunks) drain_one();
+        if (!Cfg::MERGED && nkb > 0) {
             mbar_wait(&done_bar, 0);
             tc_fence_after();
-            drain_cols(tmem_lane + (uint32_t)(2 * BN));
+            drain_cols(tmem_lane + (uint32_t)(2 * BN));            // the cross accumulator of the whole reduction
         }
         // ---- partial[split][i][j]: TMEM lane rho = q*32 + lane holds channel i = 4*lane + q; accumulator column
         //      rho_b = half*BN/2 + a holds j = 4*(rho_b % BQ) + rho_b / BQ, i.e. this thread has the column pairs

@@ -63,6 +63,7 @@ int32_t ensure_init() {
         if (st == CPB_OK) st = tc_wgrad_init();
         if (st == CPB_OK) st = tc2_tapgemm_init();
         if (st == CPB_OK) st = tc2_wgrad_init();
+        if (st == CPB_OK) st = tc3_wgrad_init();
         g_init_status[dev] = st;
         g_init_done[dev] = st == CPB_OK ? 1 : 2;
     }
@@ -407,7 +408,14 @@ static int32_t run_wgrad(const char* label, const float* big, int Wb, int pitch,
     // byte against 2 for the register path of tc_wgrad.cu, and measures 10-40 % slower (profiles/r2_cycle_accounting.md).
     // Opt in with CPB_TC2_WGRAD=1; the unit tests exercise it through cpb_debug_tc_wgrad either way.
     static const bool tc2_wg = [] { const char* e = getenv("CPB_TC2_WGRAD"); return e != nullptr && atoi(e) != 0; }();
-    if (g_math_mode == 1 && tc2_wg && tc2_wgrad_supported(w) && !(tc_debug_flags() & 32)) {
+    if (g_math_mode == 1 && tc3_wgrad_supported(w) && !(tc_debug_flags() & 32)) {
+        // J <= 64 (conv2, deconv3): A operand in tensor memory, see tc3_wgrad.cu
+        const long long tiles = (long long)cdiv(w.I, 128), boxes = tc3_wgrad_boxes(w);
+        long long sp = 148 / tiles;
+        if (sp > boxes) sp = boxes;
+        w.splits = (int)(sp < 1 ? 1 : sp);
+        CPB_TRY(launch_tc3_wgrad(w, s));
+    } else if (g_math_mode == 1 && tc2_wg && tc2_wgrad_supported(w) && !(tc_debug_flags() & 32)) {
         int bw, bh, bn; long long nboxes;
         tc2_wgrad_plan(w, bw, bh, bn, nboxes);
         w.splits = tc2_wgrad_pick_splits(w.I, w.J, nboxes);
@@ -928,6 +936,10 @@ int32_t cpb_debug_tc_wgrad(const float* big, const float* small, float* out, int
     w.ntaps = 1; w.run = i; w.tap_off[0] = 0; w.I = i; w.J = j; w.tc_variant = variant;
     w.splits = 2;
     w.m_per_split = align_up(((long long)m + 1) / 2, 32);
+    if ((variant & 128) && tc3_wgrad_available(w)) {             // variant & 128: J <= 64 kernel with the A operand in tensor memory
+        CPB_TRY(launch_tc3_wgrad(w, s));
+        return launch_reduce_partials(partial, w.splits, i, j, i, i, out, s);
+    }
     if (tc2_wgrad_supported(w) && !(variant & 32)) {       // variant & 1: descriptor probe (LBO / SBO swapped); & 32: round-1 kernel
         CPB_TRY(launch_tc2_wgrad(w, s));
         return launch_reduce_partials(partial, w.splits, i, j, i, i, out, s);

@@ -29,5 +29,11 @@ buf = C.create_string_buffer(1 << 16); n = lib.cpb_profile_report(buf, len(buf))
 rows = [ln.split() for ln in buf.raw[:n].decode().splitlines()]
 tot = sum(float(r[2]) for r in rows) / 3
 print("B=%d: %.3f ms/step (%.0f frames/s); sum of labelled groups %.3f ms" % (B, ms, B / ms * 1e3, tot))
+if os.environ.get("OUT"):
+    import json
+    with open(os.environ["OUT"], "w") as f:
+        json.dump({"per_gpu_batch": B, "ms_per_step": ms, "frames_per_s": B / ms * 1e3, "sum_of_groups_ms": tot,
+                   "groups_ms_per_step": {r[0]: round(float(r[2]) / 3, 4) for r in sorted(rows, key=lambda r: -float(r[2]))},
+                   "how": "scripts/step_profile.py: CUDA events around 10 steps; per-call-site CUDA events (cpb_profile_*) over 3 more steps"}, f, indent=1)
 for r in sorted(rows, key=lambda r: -float(r[2]))[:40]:
     print("  %-20s %8.3f ms" % (r[0], float(r[2]) / 3))

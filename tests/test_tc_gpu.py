@@ -56,8 +56,12 @@ def test_tc_gemm_positive_data_has_no_accumulation_bias():
     assert abs(np.mean((got - ref) / ref)) < 2e-6
 
 
+@pytest.mark.parametrize("variant", [32, 0, 128], ids=["register_path", "tc2_mn_major_tma", "tc3_a_in_tmem"])
 @pytest.mark.parametrize("m,i,j", [(4096, 128, 128), (5000, 256, 64), (4100, 128, 32), (1031, 384, 256)])
-def test_tc_wgrad_matches_float64(m, i, j):
+def test_tc_wgrad_matches_float64(m, i, j, variant):
+    """All three weight-gradient kernels through cpb_debug_tc_wgrad: 32 = tc_wgrad.cu (register transposes, the default in the
+    VAE step), 0 = tc2_wgrad.cu (both operands MN-major by TMA tensor maps), 128 = tc3_wgrad.cu (A operand in tensor memory,
+    J <= 64 only; other shapes fall through to tc2)."""
     import torch
     from carla_ppo_b200 import _lib
     lib = _lib.load()
@@ -67,7 +71,7 @@ def test_tc_wgrad_matches_float64(m, i, j):
     tb, ts = torch.tensor(big, device="cuda"), torch.tensor(small, device="cuda")
     out = torch.full((i, j), float("nan"), device="cuda")
     part = torch.zeros(2 * i * j, device="cuda")          # the debug entry uses 2 splits
-    _lib.check(lib.cpb_debug_tc_wgrad(tb.data_ptr(), ts.data_ptr(), out.data_ptr(), m, i, j, 0, part.data_ptr(),
+    _lib.check(lib.cpb_debug_tc_wgrad(tb.data_ptr(), ts.data_ptr(), out.data_ptr(), m, i, j, variant, part.data_ptr(),
                                       _lib.current_stream_handle()))
     torch.cuda.synchronize()
     ref = big.astype(np.float64).T @ small.astype(np.float64)
