@@ -381,6 +381,9 @@ static int32_t tg(const char* label, const TapGemmParams& p, cudaStream_t s, int
         TapGemmParams q = scatter_k > 0 ? quad_from_scatter(p, scatter_k) : p;
         q.debug = tc_debug_flags();
         if (tc2_tapgemm_supported(q, scatter_k)) return launch_tc2_tapgemm(q, scatter_k, s);     // TMA tensor maps, no lo planes
+        // with tc2 enabled the weight images are in the tc2 block order and the SIMT transposes are not written: a layer the
+        // tc2 kernel cannot take must not silently run on stale operands (cannot happen with the fixed 80x160 geometry)
+        CPB_REQUIRE(!tc2_enabled(), "layer %s is not supported by the tc2 tap-GEMM (C=%d, N=%d)", label, q.C, q.N);
         q.src_lo = src_lo != nullptr ? src_lo : tl_lo_scratch;
         q.dst_lo = dst_lo;
         if (tc_tapgemm_supported(q)) {
@@ -473,15 +476,20 @@ static int32_t relayout_weights(const VaePlan& pl, const VaeLayout& L, const flo
         j.count = mode == 0 ? (long long)taps * rows * cols : (long long)taps * rows_pad * cols;
         t.total += j.count;
     };
-    if (decoder) {
+    // the transposed conv / deconv kernels feed the SIMT scatter-form tap-GEMM only: with the tensor-core path active
+    // (math mode 1, tc2) nothing reads them, and at a 512-frame shard this launch is 1 % of the step
+    const bool simt_scatter = !(g_math_mode == 1 && tc2_enabled());
+    if (decoder && simt_scatter) {
         add(L.off[T_DECONV1_K], pl.rl.deconv1T, 16, C3, C4, 0, 0);
         add(L.off[T_DECONV2_K], pl.rl.deconv2T, 16, C2, C3, 0, 0);
         add(L.off[T_DECONV3_K], pl.rl.deconv3T, 25, C1, C2, 0, 0);
     }
-    if (backward) {
+    if (backward && simt_scatter) {
         add(L.off[T_CONV2_K], pl.rl.conv2T, 16, C1, C2, 0, 0);
         add(L.off[T_CONV3_K], pl.rl.conv3T, 16, C2, C3, 0, 0);
         add(L.off[T_CONV4_K], pl.rl.conv4T, 16, C3, C4, 0, 0);
+    }
+    if (backward) {
         add(L.off[T_DENSE1_K], pl.rl.dense1T, 1, pl.z, FEAT, 0, 0);
         add(L.off[T_MEAN_K], pl.rl.headsT, 2, FEAT, pl.z, 0, 0);   // mean and logvar kernels are adjacent
     }

@@ -23,6 +23,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    # one JSON line on stdout: whatever native libraries print meanwhile (NCCL's banner) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -89,12 +93,15 @@ def main():
         learn_ms = l0.elapsed_time(l1)
         total_ms = float(enc_ms.item()) + learn_ms
         n_used = n_roll * horizon
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps({"config": "SURVEY 8(d) config 5", "n_gpus": world, "frames_encoded": world * per_rank,
                           "encode_ms": float(enc_ms.item()), "encode_frames_per_s": world * per_rank / float(enc_ms.item()) * 1e3,
                           "rollouts": n_roll, "learn_ms_total": learn_ms, "ms_per_learn": learn_ms / n_roll,
                           "end_to_end_frames_per_s": n_used / total_ms * 1e3,
                           "allgather_bytes": int(world * per_rank * 64 * 4) if world > 1 else 0,
-                          "data": "synthetic uint8 frames resident in HBM; shipped VAE checkpoint-232 and agent checkpoint-705 weights"}))
+                          "data": "synthetic uint8 frames resident in HBM; shipped VAE checkpoint-232 and agent checkpoint-705 weights"}), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
