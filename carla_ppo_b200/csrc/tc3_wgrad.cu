@@ -50,6 +50,7 @@ struct Tc3WgParams {
     int Cb, run, Wb;                        // big channels, floats per kernel row (k * Cb), big image width
     long long big_img;
     float* partial;
+    int debug;                              // 16: per-phase clock64 accounting of the A loaders (CTA 0)
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -189,8 +190,13 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap smallmap, const __grid_cons
             ++drained;
         };
 
+        long long prof[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64();
+        const long long tstart = tlast;
+        const bool PROF = (p.debug & 16) != 0;
+#define TC3_PROF(slot) do { if (PROF) { const long long now_ = clock64(); prof[slot] += now_ - tlast; tlast = now_; } } while (0)
         for (int kb = set; kb < nkb; kb += 2) {
             const int s = kb % kStages;
+            TC3_PROF(5);
             // chunks finished two k-block pairs ago are drained while this k-block's loads are in flight
             int x0, y0, n0;
             box_origin(kb_begin + kb, x0, y0, n0);
@@ -201,6 +207,7 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap smallmap, const __grid_cons
 #pragma unroll
                 for (int qq = 0; qq < kKR; ++qq) v[qq] = (i_ok && rel_n[qq] < nleft) ? __ldg(bp + rel_off[qq]) : 0.f;
             }
+            TC3_PROF(0);
             // L2 prefetch of the k-block kPrefetchKb ahead (one 128-byte line per position and warp)
             if (kb + kPrefetchKb < nkb) {
                 int px, py, pn;
@@ -211,8 +218,11 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap smallmap, const __grid_cons
                 for (int qq = 0; qq < kKR; ++qq)
                     if (i_ok && rel_n[qq] < nleft) asm volatile("prefetch.global.L2 [%0];" ::"l"(bp + rel_off[qq]) : "memory");
             }
+            TC3_PROF(1);
             while (drained < kb / kChunkKb - 1) drain_one();
+            TC3_PROF(2);
             if (kb >= kStages) mbar_wait(&empty_bar[s], (uint32_t)((kb / kStages - 1) & 1));     // the MMAs that read this TMEM slot are done
+            TC3_PROF(3);
             tc_fence_after();
             const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ACC_COLS + s * 64);
             tmem_st32(ta, v);                              // a_hi = raw values
@@ -223,7 +233,11 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap smallmap, const __grid_cons
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_ready[s]);
+            TC3_PROF(4);
         }
+        if (PROF && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (warp == 0 || warp == 4))
+            printf("tc3prof warp %d nkb %d total %lld: issue_loads %lld prefetch %lld drain %lld wait_empty %lld wait_data+st %lld other %lld\n",
+                   warp, nkb, clock64() - tstart, prof[0], prof[1], prof[2], prof[3], prof[4], prof[5]);
         while (drained < nchunks) drain_one();
         // ---- partial[split][i][j]
         if (i_ok) {
@@ -389,6 +403,7 @@ int32_t launch_tc3_wgrad(const WgradParams& w, cudaStream_t stream) {
     p.big = w.big; p.I = w.I; p.J = w.J; p.batch = w.batch;
     p.Cb = w.big_pitch; p.run = w.run; p.Wb = dense ? 0 : w.Wb; p.big_img = w.big_img;
     p.partial = w.partial;
+    p.debug = w.tc_variant;
     alignas(64) CUtensorMap smallmap;
     const unsigned long long dims[4] = {(unsigned long long)w.J, (unsigned long long)w.Wo, (unsigned long long)w.Ho, (unsigned long long)w.batch};
     const unsigned long long strides[3] = {(unsigned long long)w.J * 4ull, (unsigned long long)w.Wo * w.J * 4ull, (unsigned long long)w.Ho * w.Wo * w.J * 4ull};

@@ -417,6 +417,7 @@ static int32_t run_wgrad(const char* label, const float* big, int Wb, int pitch,
         long long sp = 148 / tiles;
         if (sp > boxes) sp = boxes;
         w.splits = (int)(sp < 1 ? 1 : sp);
+        w.tc_variant = tc_debug_flags();
         CPB_TRY(launch_tc3_wgrad(w, s));
     } else if (g_math_mode == 1 && tc2_wg && tc2_wgrad_supported(w) && !(tc_debug_flags() & 32)) {
         int bw, bh, bn; long long nboxes;
