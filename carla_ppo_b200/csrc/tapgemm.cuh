@@ -91,7 +91,8 @@ struct TcWeightJob {
     int N, C;                   // logical rows / reduction length per tap
     long long count;
     int raw;                    // 1 (tc2 kernels): blocks ordered (n-tile y, tap, k-block): block index (y * ntaps + tap) * (C/32) + kc,
-                                // each block = [hi image | lo image] = 2*BN*32 floats (one bulk copy per k-block)
+                                // each block = [hi image | lo image] = 2*BN*32 floats (one bulk copy per k-block);
+                                // 2 (tc2, CTA-pair MMAs): same block order, block = [hi rows 0:h | lo rows 0:h | hi rows h:2h | lo rows h:2h], h = BN/2
     int ntaps;                  // taps of the operand (raw layout only)
 };
 // rows of the N axis handled per CTA tile (also fixes the block size of the stored operand)

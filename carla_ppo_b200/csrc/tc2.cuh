@@ -56,12 +56,15 @@ struct Tc2Params {
 
 // host: driver entry point for cuTensorMapEncodeTiled (resolved through the runtime, no libcuda link dependency)
 // atom32 = 0: SWIZZLE_128B (16-byte chunks XOR row % 8; K-major operands); 1: SWIZZLE_128B_ATOM_32B (32-byte chunks XOR
-// row % 4) -- the only shared-memory layout the tensor core accepts for MN-major 32-bit (TF32) operands
+// row % 4) -- the only shared-memory layout the tensor core accepts for MN-major 32-bit (TF32) operands; 2: no swizzle
+// (tiles that threads, not the tensor core, read)
 int32_t tc2_encode_tiled(CUtensorMap* map, const float* base, int rank, const unsigned long long* dims,
                          const unsigned long long* strides_bytes, const unsigned* box, const unsigned* elem_strides, int atom32 = 0);
 
 int32_t tc2_tapgemm_init();
 bool tc2_enabled();
+// layout of the weight images the tap-GEMM expects (TcWeightJob.raw): 1 = [hi image | lo image] per block, 2 = CTA-pair order
+int tc2_weight_layout();
 // Builds the tensor map + schedule for a gather / quad / dense problem described by the round-1 TapGemmParams and
 // enqueues it.  p.wk_hi must point at the RAW weight images (tc_weights mode "raw").
 int32_t launch_tc2_tapgemm(const TapGemmParams& p, int scatter_k, cudaStream_t stream);

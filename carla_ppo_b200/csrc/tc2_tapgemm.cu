@@ -2,7 +2,9 @@
 //
 //   dst[pos(m), n] = epilogue( sum_kb  A_kb[m, 0:32] . W_kb[n, 0:32] ),     a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo
 //
-// Persistent, warp-specialised, one CTA per SM in clusters of CS CTAs that share the weight tiles:
+// Persistent, warp-specialised, one CTA per SM in clusters of CS CTAs that share the weight tiles.  Default (CS = 2,
+// CPB_TC_PAIR=1): the two CTAs form a tcgen05 CTA PAIR -- one elected lane of the leader CTA issues cta_group::2 MMAs
+// (M = 256) for both SMs, each CTA stages only its half of the weight tile (see Tc2Cfg), which makes room for a 4th stage:
 //   warp 13      producer: per k-block ONE cp.async.bulk.tensor (TMA tensor map: the [positions x 32 floats] box of the
 //                activation tile, 128-byte rows, SWIZZLE_128B, out-of-image positions zero-filled by the copy engine) and
 //                ONE cp.async.bulk slice of the pre-swizzled, pre-split weight image [b_hi | b_lo], multicast to the cluster; both complete on the
@@ -25,17 +27,26 @@ namespace {
 
 using namespace tc;
 
-template <int BN>
+// PAIR: the two CTAs of a cluster run ONE tcgen05.mma.cta_group::2 stream (M = 256: 128 rows per CTA).  Each CTA then
+// stages only ITS half of the weight tile -- rows [r*BN/2, (r+1)*BN/2) of b_hi and of b_lo, adjacent -- and the tensor
+// cores read each half once for both SMs: a k-block costs a CTA 16 KB (A) + 16 KB (a_lo) + BN*128 B (weights) of shared
+// memory instead of + 2*BN*128 B, which buys the 4th pipeline stage at BN = 128 and cuts the operand reads per MMA
+// (profiles/r2_cycle_accounting.md: the 1-CTA kernel saturates the shared-memory data path, not the tensor pipe).
+// Accumulator columns of a buffer (h = BN/2):  [m0 | c0 | m1 | c1]  <-  a_hi x {CTA0: [b_hi 0:h | b_lo 0:h], CTA1: [b_hi h:2h | b_lo h:2h]};
+// the third product a_lo x b_hi (N = BN, h rows from each CTA) lands on columns [h, h + BN) = [c0 | m1]: both are summed
+// into the same outputs by the drain.
+template <int BN, bool PAIR>
 struct Tc2Cfg {
     static constexpr int B_TILE_BYTES = BN * TBK * 4;
-    static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;     // [A_hi | A_lo | B_hi | B_lo]
+    static constexpr int B_STAGE_BYTES = PAIR ? B_TILE_BYTES : 2 * B_TILE_BYTES;
+    static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + B_STAGE_BYTES;         // [A_hi | A_lo | B_hi | B_lo]
     static constexpr int STAGES = (STAGE_BYTES * 4 <= 200 * 1024) ? 4 : 3;
     static constexpr int SLICE = BN / 2 < 32 ? BN / 2 : 32;                      // columns transposed per epilogue pass
     static constexpr int STAGING_BYTES = 8 * 32 * SLICE * 4;                     // 8 drain warps x [32 rows x SLICE floats]
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024;
     // TSA (BN <= 64): the A operand of both MMAs is read from TENSOR MEMORY, not shared memory: the splitters move each
     // k-block's rows (raw = hi, and lo) into TMEM columns with tcgen05.st, 2 x 32 columns per stage, next to the accumulators
-    static constexpr bool TSA = BN <= 64;
+    static constexpr bool TSA = BN <= 64 && !PAIR;
     static constexpr int ACC_COLS = 4 * BN;
     static constexpr int TMEM_NEED = ACC_COLS + (TSA ? STAGES * 64 : 0);
     static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
@@ -55,6 +66,7 @@ constexpr int kThreads = 448;
 int g_cluster = 2;
 int g_resident[3] = {0, 0, 0};
 int g_enabled = 1;
+int g_pair = 1;                  // CTA-pair MMAs (cta_group::2, CPB_TC_PAIR, default on); needs clusters of exactly 2
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
@@ -109,12 +121,44 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
         : "memory");
 }
 
+// ---- CTA-pair (cta_group::2) flavours
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc2(uint32_t* slot) {      // one warp of EACH CTA of the pair, same slot offset
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(NCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc2(uint32_t base) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(NCOLS) : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// completion of every MMA issued so far -> the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// arrive on the barrier at this offset in CTA `cta` of the cluster.  Plain form on purpose: `.release.cluster` compiles to
+// MEMBAR.ALL.GPU (measured: +650 clk per k-block, the splitters became the bottleneck) and is not needed -- what the
+// waiter triggers is the ARRIVING CTA's own tensor core reading that CTA's shared / tensor memory, and the arriving
+// thread has already fenced those writes (fence.proxy.async / tcgen05.fence::before_thread_sync) before this instruction.
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
 #define TC2_PROF(slot) do { if constexpr (PROF) { const long long now_ = clock64(); prof[slot] += now_ - tlast; tlast = now_; } } while (0)
 
-template <int BN, bool PROF>
+template <int BN, bool PAIR, bool PROF>
 __global__ void __launch_bounds__(kThreads, 1)
 tc2_tapgemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ Tc2Params p, const int mtiles, const int total_st) {
-    using Cfg = Tc2Cfg<BN>;
+    using Cfg = Tc2Cfg<BN, PAIR>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int B_TILE_BYTES = Cfg::B_TILE_BYTES;
     constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
@@ -127,6 +171,8 @@ tc2_tapgemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
     __shared__ uint64_t chunk_bar[2];         // tensor core -> drain warps
     __shared__ uint64_t drained_bar[2];       // drain warps -> issuer
     __shared__ uint32_t tmem_slot;
+    // PROF: per-stage time stamps of the refill cycle (commit -> copies issued -> full -> ready -> MMAs issued)
+    __shared__ long long ts_commit[PROF ? 4 : 1], ts_issue[PROF ? 4 : 1], ts_ready[PROF ? 4 : 1];
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -142,12 +188,20 @@ tc2_tapgemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&ready_bar[s], kSplitWarps); mbar_init(&empty_bar[s], (uint32_t)CS); }
+        // PAIR: ready / drained live in the leader CTA and collect the arrivals of both CTAs; one multicast commit frees a stage in both
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&ready_bar[s], (uint32_t)((PAIR ? 2 : 1) * kSplitWarps));
+            mbar_init(&empty_bar[s], PAIR ? 1u : (uint32_t)CS);
+        }
         mbar_init(&chunk_bar[0], 1); mbar_init(&chunk_bar[1], 1);
-        mbar_init(&drained_bar[0], kDrainWarps); mbar_init(&drained_bar[1], kDrainWarps);
+        mbar_init(&drained_bar[0], PAIR ? 2 * kDrainWarps : kDrainWarps); mbar_init(&drained_bar[1], PAIR ? 2 * kDrainWarps : kDrainWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) tmem_alloc<Cfg::TMEM_COLS>(&tmem_slot);
+    if (warp == 0) {
+        if constexpr (PAIR) tmem_alloc2<Cfg::TMEM_COLS>(&tmem_slot);
+        else tmem_alloc<Cfg::TMEM_COLS>(&tmem_slot);
+    }
     tc_fence_before();
     __syncthreads();
     if (CS > 1) cluster_sync_all();
@@ -167,8 +221,10 @@ tc2_tapgemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
         // ================================ producer ================================
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&amap)) : "memory");
-            const uint32_t slice = (uint32_t)(2 * B_TILE_BYTES / CS);      // [b_hi | b_lo] images, pre-split by tc_weights_kernel
-            const uint32_t tx_bytes = (uint32_t)(((p.debug & 2) ? 0 : box_rows * 128) + 2 * B_TILE_BYTES);   // debug 2: no A copies (timing)
+            // 1-CTA MMAs: every CTA copies 1/CS of the [b_hi | b_lo] block and multicasts it; PAIR: the CTA's own half block
+            // ([b_hi rows of this CTA | b_lo rows of this CTA], tc_weights_kernel raw = 2), no multicast
+            const uint32_t slice = (uint32_t)(2 * B_TILE_BYTES / CS);
+            const uint32_t tx_bytes = (uint32_t)(((p.debug & 2) ? 0 : box_rows * 128) + Cfg::B_STAGE_BYTES);   // debug 2: no A copies (timing)
             // The activation tiles come from HBM (GBs per layer, nothing is L2-resident): a copy issued when its stage
             // frees up would expose the full DRAM latency to a ring of only 3-4 stages.  A second cursor therefore runs
             // kPrefetchKb k-blocks ahead and pulls the boxes into L2 (cp.async.bulk.prefetch.tensor), no shared memory needed.
@@ -184,6 +240,9 @@ tc2_tapgemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
             pf_origin();
             for (int i = 0; i < kPrefetchKb; ++i) pf_step();
             int g = 0;
+            long long prof[4] = {0, 0, 0, 0}, tlast = 0;
+            if constexpr (PROF) tlast = clock64();
+            const long long tstart = tlast;
             for (int st = cl_id; st < total_st; st += cl_n) {
                 int x0, y0, n0;
                 mt_origin(st_mt(st), x0, y0, n0);
@@ -192,12 +251,23 @@ tc2_tapgemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
                 for (int kb = 0; kb < nkb; ++kb, ++g) {
                     const int s = g % STAGES;
                     pf_step();
+                    TC2_PROF(1);
                     if (g >= STAGES) mbar_wait(&empty_bar[s], (uint32_t)((g / STAGES - 1) & 1));
+                    TC2_PROF(0);
+                    if constexpr (PROF) { if (g >= STAGES) prof[3] += clock64() - ts_commit[s]; }
                     const uint32_t stage = smem_base + s * STAGE_BYTES;
                     mbar_expect_tx(&full_bar[s], tx_bytes);
                     if (!(p.debug & 2)) tma_load_4d(stage, &amap, p.kb[kb].c, x0 + p.kb[kb].dx, y0 + p.kb[kb].dy, n0, &full_bar[s]);
-                    bulk_g2s(stage + 2 * A_TILE_BYTES + (uint32_t)rank * slice, wt + (size_t)kb * (2 * B_TILE_BYTES), slice, &full_bar[s], cl_mask, CS > 1);
+                    bulk_g2s(stage + 2 * A_TILE_BYTES + (PAIR ? 0u : (uint32_t)rank * slice), wt + (size_t)kb * (2 * B_TILE_BYTES), slice, &full_bar[s], cl_mask,
+                             !PAIR && CS > 1);
+                    if constexpr (PROF) ts_issue[s] = clock64();
+                    TC2_PROF(2);
                 }
+            }
+            if constexpr (PROF) {
+                if (blockIdx.x == 0)
+                    printf("tc2prof   producer total %lld: wait_empty %lld prefetch %lld issue_copies %lld | commit->producer awake %lld per kb\n", clock64() - tstart, prof[0], prof[1], prof[2],
+                           prof[3] / (g > STAGES ? g - STAGES : 1));
             }
         }
         __syncwarp();
@@ -209,10 +279,15 @@ tc2_tapgemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
         // shared-memory bandwidth, which is what bounds this kernel (profiles/r2_cycle_accounting.md).
         const int tl = tid - kSplitWarp0 * 32;
         int g = 0;
+        long long prof[4] = {0, 0, 0, 0}, tlast = 0;
+        if constexpr (PROF) tlast = clock64();
+        const long long tstart = tlast;
         for (int st = cl_id; st < total_st; st += cl_n) {
             for (int kb = 0; kb < nkb; ++kb, ++g) {
                 const int s = g % STAGES;
                 mbar_wait(&full_bar[s], (uint32_t)((g / STAGES) & 1));
+                TC2_PROF(0);
+                if constexpr (PROF) { if (tid == kSplitWarp0 * 32) prof[2] += clock64() - ts_issue[s]; }
                 const uint32_t stage = smem_base + s * STAGE_BYTES;
                 if constexpr (Cfg::TSA) {
                     // row tl of the tile (8 swizzled 16-byte chunks, conflict-free per quarter-warp) -> registers -> TMEM:
@@ -241,16 +316,27 @@ tc2_tapgemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
                 }
                 fence_async_smem();          // generic-proxy writes (lo tiles) -> visible to the tensor core's async-proxy reads
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&ready_bar[s]);
+                if (lane == 0) {
+                    if constexpr (PAIR) mbar_arrive_cta(&ready_bar[s], 0u);
+                    else mbar_arrive(&ready_bar[s]);
+                    if constexpr (PROF) { if (warp == kSplitWarp0 + kSplitWarps - 1) ts_ready[s] = clock64(); }
+                }
+                TC2_PROF(1);
             }
+        }
+        if constexpr (PROF) {
+            if (blockIdx.x == 0 && tid == kSplitWarp0 * 32)
+                printf("tc2prof   splitter total %lld: wait_full %lld split+arrive %lld | copies issued->full (observed) %lld per kb\n", clock64() - tstart, prof[0], prof[1], prof[2] / (g > 0 ? g : 1));
         }
     } else if (warp == kIssuerWarp) {
         // ================================ MMA issuer ================================
-        if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
-            const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+        // PAIR: only the leader CTA (rank 0) issues; every instruction drives the tensor cores of both SMs
+        if (lane == 0 && (!PAIR || rank == 0)) {
+            constexpr uint32_t MDIM = PAIR ? 2u * TBM : (uint32_t)TBM;
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((MDIM >> 4) << 24);
+            const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((MDIM >> 4) << 24);
             int g = 0, gc = 0;
-            long long prof[4] = {0, 0, 0, 0}, tlast = 0;
+            long long prof[4] = {0, 0, 0, 0}, tlast = 0, lat_sum = 0;
             if constexpr (PROF) tlast = clock64();
             const long long tstart = tlast;
             for (int st = cl_id; st < total_st; st += cl_n) {
@@ -261,6 +347,8 @@ tc2_tapgemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
                     TC2_PROF(3);
                     mbar_wait(&ready_bar[s], (uint32_t)((g / STAGES) & 1));
                     TC2_PROF(0);
+                    long long lat_ready = 0;
+                    if constexpr (PROF) lat_ready = clock64() - ts_ready[s];
                     if (kb % CHUNK_KB == 0 && gc >= 2)
                         mbar_wait(&drained_bar[b], (uint32_t)(((gc >> 1) - 1) & 1));
                     TC2_PROF(1);
@@ -269,33 +357,47 @@ tc2_tapgemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
                     const uint64_t a_lo = make_desc(stage + A_TILE_BYTES);
                     const uint64_t b_hi = make_desc(stage + 2 * A_TILE_BYTES);     // [b_hi | b_lo] adjacent: one N = 2*BN operand
                     const uint32_t d_main = tmem_base + (uint32_t)(b * 2 * BN);
-                    const uint32_t d_cross = d_main + (uint32_t)BN;
-                    if constexpr (Cfg::TSA) {
-                        const uint32_t ta = tmem_base + (uint32_t)(Cfg::ACC_COLS + s * 64);
+                    const uint32_t d_cross = d_main + (uint32_t)(PAIR ? BN / 2 : BN);   // PAIR: columns [c0 | m1], see Tc2Cfg
+                    if constexpr (PAIR) {
                         if (!(p.debug & 1))
 #pragma unroll
                         for (int ks = 0; ks < TBK / 8; ++ks) {
                             const uint64_t adv = (uint64_t)(ks * 2);
-                            umma_tf32_ts(d_main, ta + (uint32_t)(ks * 8), b_hi + adv, idesc2, ((kb % CHUNK_KB) | ks) != 0 ? 1u : 0u);
-                            umma_tf32_ts(d_cross, ta + 32u + (uint32_t)(ks * 8), b_hi + adv, idesc, 1u);
+                            umma2_tf32(d_main, a_hi + adv, b_hi + adv, idesc2, ((kb % CHUNK_KB) | ks) != 0 ? 1u : 0u);
+                            umma2_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, 1u);
                         }
-                    } else if (!(p.debug & 1)) {
+                        umma2_commit(&empty_bar[s]);
+                        if constexpr (PROF) { ts_commit[s] = clock64(); lat_sum += lat_ready; }
+                        if (kb % CHUNK_KB == CHUNK_KB - 1 || kb == nkb - 1) { umma2_commit(&chunk_bar[b]); ++gc; }
+                    } else {
+                        if constexpr (Cfg::TSA) {
+                            const uint32_t ta = tmem_base + (uint32_t)(Cfg::ACC_COLS + s * 64);
+                            if (!(p.debug & 1))
 #pragma unroll
-                        for (int ks = 0; ks < TBK / 8; ++ks) {
-                            const uint64_t adv = (uint64_t)(ks * 2);
-                            umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc2, ((kb % CHUNK_KB) | ks) != 0 ? 1u : 0u);
-                            umma_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, 1u);
+                            for (int ks = 0; ks < TBK / 8; ++ks) {
+                                const uint64_t adv = (uint64_t)(ks * 2);
+                                umma_tf32_ts(d_main, ta + (uint32_t)(ks * 8), b_hi + adv, idesc2, ((kb % CHUNK_KB) | ks) != 0 ? 1u : 0u);
+                                umma_tf32_ts(d_cross, ta + 32u + (uint32_t)(ks * 8), b_hi + adv, idesc, 1u);
+                            }
+                        } else if (!(p.debug & 1)) {
+#pragma unroll
+                            for (int ks = 0; ks < TBK / 8; ++ks) {
+                                const uint64_t adv = (uint64_t)(ks * 2);
+                                umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc2, ((kb % CHUNK_KB) | ks) != 0 ? 1u : 0u);
+                                umma_tf32(d_cross, a_lo + adv, b_hi + adv, idesc, 1u);
+                            }
                         }
+                        umma_commit_mc(&empty_bar[s], cl_mask, CS > 1);
+                        if constexpr (PROF) { ts_commit[s] = clock64(); lat_sum += lat_ready; }
+                        if (kb % CHUNK_KB == CHUNK_KB - 1 || kb == nkb - 1) { umma_commit(&chunk_bar[b]); ++gc; }
                     }
-                    umma_commit_mc(&empty_bar[s], cl_mask, CS > 1);
-                    if (kb % CHUNK_KB == CHUNK_KB - 1 || kb == nkb - 1) { umma_commit(&chunk_bar[b]); ++gc; }
                     TC2_PROF(2);
                 }
             }
             if constexpr (PROF) {
                 if (blockIdx.x == 0)
-                    printf("tc2prof BN=%d N=%d nkb=%d quad=%d box=%dx%dx%d supertiles=%d cluster=%d kb/cta=%d | issuer total %lld: wait_ready %lld wait_drained %lld issue %lld other %lld\n",
-                           BN, p.N, nkb, p.quad, p.bw, p.bh, p.bn, total_st, CS, g, clock64() - tstart, prof[0], prof[1], prof[2], prof[3]);
+                    printf("tc2prof BN=%d N=%d nkb=%d quad=%d box=%dx%dx%d supertiles=%d cluster=%d pair=%d stages=%d kb/cta=%d | issuer total %lld: wait_ready %lld wait_drained %lld issue %lld other %lld | ready(last splitter of this CTA)->issuer awake %lld per kb\n",
+                           BN, p.N, nkb, p.quad, p.bw, p.bh, p.bn, total_st, CS, PAIR ? 1 : 0, STAGES, g, clock64() - tstart, prof[0], prof[1], prof[2], prof[3], lat_sum / (g > 0 ? g : 1));
             }
         }
         __syncwarp();
@@ -304,7 +406,9 @@ tc2_tapgemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
         constexpr int HALF_COLS = BN / 2;
         const int q = warp & 3;
         const int half = warp >> 2;
-        const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * HALF_COLS);
+        // this warp's output columns [half*HALF_COLS, +HALF_COLS): main at accumulator column ..., its cross term CROSS_OFF further
+        constexpr int CROSS_OFF = PAIR ? HALF_COLS : BN;                       // PAIR: [m0 | c0 | m1 | c1] with h = HALF_COLS
+        const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (PAIR ? 2 * HALF_COLS : HALF_COLS));
         float acc[HALF_COLS];
 #pragma unroll
         for (int i = 0; i < HALF_COLS; ++i) acc[i] = 0.f;
@@ -439,10 +543,13 @@ tc2_tapgemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
             TC2_PROF(0);
             tc_fence_after();
             drain_cols(tmem_lane + (uint32_t)(b * 2 * BN));
-            drain_cols(tmem_lane + (uint32_t)(b * 2 * BN + BN));
+            drain_cols(tmem_lane + (uint32_t)(b * 2 * BN + CROSS_OFF));
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&drained_bar[b]);
+            if (lane == 0) {
+                if constexpr (PAIR) mbar_arrive_cta(&drained_bar[b], 0u);
+                else mbar_arrive(&drained_bar[b]);
+            }
             ++drained;
             TC2_PROF(1);
             if (--chunksD == 0) {
@@ -463,25 +570,28 @@ tc2_tapgemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
     tc_fence_before();
     __syncthreads();
     if (CS > 1) cluster_sync_all();
-    if (warp == 0) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if (warp == 0) {
+        if constexpr (PAIR) tmem_dealloc2<Cfg::TMEM_COLS>(tmem_base);
+        else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    }
     (void)mtiles;
 }
 
 constexpr int bn_slot(int BN) { return BN == 128 ? 2 : (BN == 64 ? 1 : 0); }
 
-template <int BN, bool PROF>
+template <int BN, bool PAIR, bool PROF>
 int32_t launch_t(const CUtensorMap& map, const Tc2Params& p, int mtiles, int total_st, unsigned grid, cudaStream_t stream) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = Tc2Cfg<BN>::SMEM_BYTES;
+    cfg.dynamicSmemBytes = Tc2Cfg<BN, PAIR>::SMEM_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeClusterDimension;
     attr.val.clusterDim.x = (unsigned)p.cluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr; cfg.numAttrs = 1;
-    CPB_CUDA(cudaLaunchKernelEx(&cfg, tc2_tapgemm_kernel<BN, PROF>, map, p, mtiles, total_st));
+    CPB_CUDA(cudaLaunchKernelEx(&cfg, tc2_tapgemm_kernel<BN, PAIR, PROF>, map, p, mtiles, total_st));
     CPB_LAUNCHED();
     return CPB_OK;
 }
@@ -496,15 +606,19 @@ int32_t launch_bn(const CUtensorMap& map, Tc2Params& p, cudaStream_t stream) {
     const int resident = g_resident[bn_slot(BN)];
     CPB_REQUIRE(total_st < (1ll << 30) && resident > 0, "tc2_tapgemm: bad tile count");
     const unsigned grid = (unsigned)((total_st < resident ? total_st : resident) * p.cluster);
-    if (p.debug & 16) return launch_t<BN, true>(map, p, (int)mtiles, (int)total_st, grid, stream);
-    return launch_t<BN, false>(map, p, (int)mtiles, (int)total_st, grid, stream);
+    if (g_pair) {
+        if (p.debug & 16) return launch_t<BN, true, true>(map, p, (int)mtiles, (int)total_st, grid, stream);
+        return launch_t<BN, true, false>(map, p, (int)mtiles, (int)total_st, grid, stream);
+    }
+    if (p.debug & 16) return launch_t<BN, false, true>(map, p, (int)mtiles, (int)total_st, grid, stream);
+    return launch_t<BN, false, false>(map, p, (int)mtiles, (int)total_st, grid, stream);
 }
 
-template <int BN>
-int32_t init_one() {
-    using Cfg = Tc2Cfg<BN>;
-    CPB_CUDA(cudaFuncSetAttribute(tc2_tapgemm_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    CPB_CUDA(cudaFuncSetAttribute(tc2_tapgemm_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+template <int BN, bool PAIR>
+int32_t init_pair() {
+    using Cfg = Tc2Cfg<BN, PAIR>;
+    CPB_CUDA(cudaFuncSetAttribute(tc2_tapgemm_kernel<BN, PAIR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    CPB_CUDA(cudaFuncSetAttribute(tc2_tapgemm_kernel<BN, PAIR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(g_cluster * 1024));
@@ -515,10 +629,15 @@ int32_t init_one() {
     attr.val.clusterDim.x = (unsigned)g_cluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr; cfg.numAttrs = 1;
     int n = 0;
-    CPB_CUDA(cudaOccupancyMaxActiveClusters(&n, tc2_tapgemm_kernel<BN, false>, &cfg));
+    CPB_CUDA(cudaOccupancyMaxActiveClusters(&n, tc2_tapgemm_kernel<BN, PAIR, false>, &cfg));
     CPB_REQUIRE(n > 0, "tc2_tapgemm: no resident cluster of %d CTAs possible", g_cluster);
     g_resident[bn_slot(BN)] = n;
     return CPB_OK;
+}
+
+template <int BN>
+int32_t init_one() {
+    return g_pair ? init_pair<BN, true>() : init_pair<BN, false>();
 }
 
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
@@ -548,7 +667,8 @@ int32_t tc2_encode_tiled(CUtensorMap* map, const float* base, int rank, const un
     for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = elem_strides[i]; }
     for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
     const CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), gd, gs, bx, es,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                atom32 == 2 ? CU_TENSOR_MAP_SWIZZLE_NONE : (atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u] estr [%u,%u,%u,%u]", (int)r, rank,
@@ -560,6 +680,7 @@ int32_t tc2_encode_tiled(CUtensorMap* map, const float* base, int rank, const un
 }
 
 bool tc2_enabled() { return g_enabled != 0 && g_encode != nullptr; }
+int tc2_weight_layout() { return g_pair ? 2 : 1; }
 
 int32_t tc2_tapgemm_init() {
     const char* e = getenv("CPB_TC2");
@@ -567,6 +688,8 @@ int32_t tc2_tapgemm_init() {
     e = getenv("CPB_TC_CLUSTER");
     g_cluster = e ? atoi(e) : 2;
     CPB_REQUIRE(g_cluster == 1 || g_cluster == 2 || g_cluster == 4 || g_cluster == 8, "CPB_TC_CLUSTER must be 1, 2, 4 or 8");
+    e = getenv("CPB_TC_PAIR");
+    g_pair = (e ? atoi(e) : 1) != 0 && g_cluster == 2;
     if (g_encode == nullptr) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;

@@ -6,19 +6,28 @@
 // Every SS-mode 3xTF32 kernel in this library is bound by the 128 B/clk of shared-memory bandwidth (operand staging +
 // the tensor core's own operand reads; profiles/r2_cycle_accounting.md), and in the weight gradient the 128-channel A tile
 // is two thirds of that traffic.  Here A never touches shared memory:
-//   * an A loader thread owns ONE channel i (= its TMEM lane) and reads its value at the 32 positions of a k-block with 32
-//     LDG.32 -- across a warp that is one coalesced 128-byte line per position (the 32 channels of a pixel are contiguous in
-//     NHWC), so no transpose exists anywhere: the access pattern itself puts the reduction index on the TMEM columns;
+//   * the copy engine brings the k-block's A values to shared memory as they lie in NHWC memory: per 32 channels one TMA
+//     tensor-map box [32 positions x 32 floats] (128-byte rows, no swizzle, stride-2 traversal of the window origins,
+//     images past the batch zero-filled) -- 4 boxes = 16 KB per k-block, written once and read once;
+//   * an A loader thread owns ONE channel i (= its TMEM lane) and picks its value at the 32 positions with 32 LDS.32 --
+//     across a warp one conflict-free 128-byte row per position, so no transpose exists anywhere: the access pattern itself
+//     puts the reduction index on the TMEM columns.  (The first version read these values with LDG.32 straight from global
+//     memory: 128 scattered 128-byte requests per warp and k-block saturated the LSU's miss path -- ~2.2 k clk per k-block
+//     just to ISSUE them, `tc3prof` in profiles/r2_cycle_accounting.md -- 3x slower than the register-transpose kernel.)
 //   * the 32 values (= a_hi, the tensor core ignores the 13 low mantissa bits) and their residuals a_lo = a - trunc_tf32(a)
 //     go to the stage's 2 x 32 TMEM columns with two tcgen05.st;  the MMAs read A from TMEM (TS form);
 //   * B (J <= 64 channels of `small`) is MN-major in shared memory: one TMA tensor-map box [32 positions x 32 floats] per
 //     32-wide column group (SWIZZLE_128B_ATOM_32B, see tc2_wgrad.cu), b_lo derived in shared memory by two splitter warps.
-// Per 32 positions the shared-memory traffic drops from ~26 KB (register path of tc_wgrad.cu, BN = 64) to ~12 KB and the LSU
-// executes 128 LDG.32 warp instructions instead of 64 LDG.128 + 128 STS.128 + the 4x4 register transposes.
+// Shared-memory traffic per 32 positions (BN = 64): A 16 KB written + 16 KB read, B 8 + 8 + 8 KB staged and 24 KB of MMA
+// operand reads = 80 KB against ~104 KB of the register path, and the LSU executes 128 LDS.32 warp instructions instead of
+// 64 LDG.128 + 128 STS.128 + the 4x4 register transposes.
 //
-// Warp roles (512 threads): warps 0-7 A loaders + accumulator drain (set = warp / 4 takes the k-blocks with kb % 2 == set;
-// both sets cover lane quarters 0-3), warp 8 MMA issuer, warp 9 B producer (TMA + L2 prefetch), warps 10-11 B splitters,
-// warps 12-15 idle.  One wave of split-K CTAs; reduce_partials() sums the splits in a fixed order.
+// Warp roles (512 threads): warps 0-7 A loaders (set = warp / 4 takes the k-blocks with kb % 2 == set; both sets cover lane
+// quarters 0-3), warp 8 MMA issuer, warp 9 producer (one lane: the B boxes and the A run boxes of every k-block), warps 10-11
+// B splitters, warps 12-15 accumulator drain (lane quarters 0-3).  Rings: A 6 stages in shared memory + 4 slots in tensor
+// memory, B 6 stages -- deep enough to cover the HBM latency of operands that stream exactly once, so there is no separate
+// L2 prefetch (neither cp.async.bulk.prefetch.tensor nor prefetch.global.L2 changed the time once the rings were this deep).
+// One wave of split-K CTAs; reduce_partials() sums the splits in a fixed order.
 #include <cuda.h>
 
 #include "tc2.cuh"
@@ -35,11 +44,13 @@ constexpr int kIssuerWarp = 8;
 constexpr int kProducerWarp = 9;
 constexpr int kSplitWarp0 = 10;
 constexpr int kSplitWarps = 2;
+constexpr int kDrainWarp0 = 12;
+constexpr int kDrainWarps = 4;
 constexpr int kThreads = 512;
 constexpr int kStages = 4;                 // TMEM: 4 x 64 columns of A next to 4 * BN accumulator columns
 constexpr int kKR = 32;                    // positions per k-block (= TMEM columns of one A plane)
 constexpr int kChunkKb = 4;
-constexpr int kPrefetchKb = 8;
+constexpr int kPrefetchKb = 10;            // k-blocks the L2 prefetch (drain warps, between chunks) runs ahead of the producer
 
 struct Tc3WgParams {
     const float* big;
@@ -48,10 +59,37 @@ struct Tc3WgParams {
     long long boxes_per_split, nboxes;
     int I, J, batch;
     int Cb, run, Wb;                        // big channels, floats per kernel row (k * Cb), big image width
+    int sx;                                 // big pixels per position step (2: stride-2 windows, 1: dense)
+    const float* small;
+    int Wo, Ho;                             // small-image grid
     long long big_img;
     float* partial;
     int debug;                              // 16: per-phase clock64 accounting of the A loaders (CTA 0)
 };
+constexpr uint32_t kAGroupBytes = kKR * 128;                  // one A channel group: 32 positions x 32 floats
+constexpr uint32_t kAStageBytes = 4 * kAGroupBytes;           // 128 channels
+constexpr int kAStages = 7;                                   // shared-memory ring of the A boxes (deeper than the TMEM ring)
+constexpr int kBStages = 7;                                   // shared-memory ring of the B boxes
+// tensor maps of `big` by box width: m[w - 1] loads boxes of 32 * w floats per position (w = 1..4 channel groups)
+struct Tc3BigMaps {
+    alignas(64) CUtensorMap m[4];
+};
+// the <= 4 channel groups of a 128-row tile form runs that are contiguous in memory (same kernel row): one TMA box per run
+struct Tc3Seg {
+    int g0, ng, kh, off0;
+};
+__device__ __forceinline__ int tile_segments(int i0, int I, int run, Tc3Seg* seg) {
+    int n = 0;
+    for (int g = 0; g < 4; ++g) {
+        const int ig = i0 + 32 * g;
+        if (ig >= I) break;
+        const int kh = ig / run, off = ig - kh * run;
+        if (n > 0 && seg[n - 1].kh == kh) { ++seg[n - 1].ng; continue; }
+        seg[n].g0 = g; seg[n].ng = 1; seg[n].kh = kh; seg[n].off0 = off;
+        ++n;
+    }
+    return n;
+}
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -90,7 +128,7 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
-tc3_wgrad_kernel(const __grid_constant__ CUtensorMap smallmap, const __grid_constant__ Tc3WgParams p) {
+tc3_wgrad_kernel(const __grid_constant__ CUtensorMap smallmap, const __grid_constant__ Tc3BigMaps bigmaps, const __grid_constant__ Tc3WgParams p) {
     constexpr int NGB = BN / 32;
     constexpr int ACC_COLS = 4 * BN;                          // 2 chunk buffers x (main | cross)
     constexpr int TMEM_COLS = 512;                            // ACC_COLS (<= 256) + kStages * 64 = 512 at BN = 64
@@ -99,24 +137,20 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap smallmap, const __grid_cons
     constexpr uint32_t STAGE_BYTES = GROUP_BYTES * 2 * NGB;   // [B_hi x NGB | B_lo x NGB]
 
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t b_full[kStages], b_ready[kStages], a_ready[kStages], empty_bar[kStages];
+    __shared__ uint64_t b_full[kBStages], b_ready[kBStages], b_empty[kBStages];      // B ring (shared memory)
+    __shared__ uint64_t a_full[kAStages], a_free[kAStages];   // A ring (shared memory): boxes landed / read out by the 4 loader warps
+    __shared__ uint64_t a_ready[kStages], empty_bar[kStages]; // A ring (tensor memory): slot written / its MMAs retired
     __shared__ uint64_t chunk_bar[2], drained_bar[2];
     __shared__ uint32_t tmem_slot;
-    __shared__ long long rel_off[kKR];      // window origin of box position q relative to the box origin (floats)
-    __shared__ int rel_n[kKR];              // image index of box position q relative to the box origin
+    __shared__ int progress;                                  // k-block the producer has reached (L2 prefetch pacing)
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    if (tid < kKR) {
-        const int bwh = p.bw * p.bh;
-        const int nn = tid / bwh, rr = tid - nn * bwh;
-        const int yy = rr / p.bw, xx = rr - yy * p.bw;
-        rel_n[tid] = nn;
-        rel_off[tid] = (long long)nn * p.big_img + ((long long)(2 * yy) * p.Wb + 2 * xx) * p.Cb;
-    }
+    if (tid == 0) progress = 0;
     const int i0 = blockIdx.x * TBM;
     const int j0 = blockIdx.y * BN;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_base = smem_base + (uint32_t)kBStages * STAGE_BYTES;    // A stages behind the B stages
     const long long kb_begin = (long long)blockIdx.z * p.boxes_per_split;
     long long kb_end = kb_begin + p.boxes_per_split;
     if (kb_end > p.nboxes) kb_end = p.nboxes;
@@ -125,11 +159,13 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap smallmap, const __grid_cons
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < kStages; ++s) {
-            mbar_init(&b_full[s], 1); mbar_init(&b_ready[s], kSplitWarps); mbar_init(&a_ready[s], 4); mbar_init(&empty_bar[s], 1);
-        }
+        for (int s = 0; s < kStages; ++s) { mbar_init(&a_ready[s], 4); mbar_init(&empty_bar[s], 1); }
+#pragma unroll
+        for (int s = 0; s < kBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_ready[s], kSplitWarps); mbar_init(&b_empty[s], 1); }
+#pragma unroll
+        for (int s = 0; s < kAStages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_free[s], 4); }
         mbar_init(&chunk_bar[0], 1); mbar_init(&chunk_bar[1], 1);
-        mbar_init(&drained_bar[0], kLoaderWarps); mbar_init(&drained_bar[1], kLoaderWarps);
+        mbar_init(&drained_bar[0], kDrainWarps); mbar_init(&drained_bar[1], kDrainWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc<TMEM_COLS>(&tmem_slot);
@@ -138,91 +174,63 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap smallmap, const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
 
-    // box index -> origin (x fastest)
-    auto box_origin = [&](long long b, int& x0, int& y0, int& n0) {
-        const int tx = (int)(b % p.tiles_x);
-        const long long r = b / p.tiles_x;
-        x0 = tx * p.bw; y0 = (int)(r % p.tiles_y) * p.bh; n0 = (int)(r / p.tiles_y) * p.bn;
+    // Box cursor: box index -> origin (x fastest), advanced incrementally -- a 64-bit div/mod chain per k-block in the single
+    // producer lane costs more than the k-block's MMAs (it did: the first version of this kernel).
+    struct Cursor {
+        int tx, ty, tn;
     };
+    auto cursor_at = [&](long long b) {
+        Cursor c;
+        c.tx = (int)(b % p.tiles_x);
+        const long long r = b / p.tiles_x;
+        c.ty = (int)(r % p.tiles_y); c.tn = (int)(r / p.tiles_y);
+        return c;
+    };
+    auto cursor_next = [&](Cursor& c) {
+        if (++c.tx == p.tiles_x) { c.tx = 0; if (++c.ty == p.tiles_y) { c.ty = 0; ++c.tn; } }
+    };
+    const bool PROF = (p.debug & 16) != 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+#define TC3_PROF(slot) do { if (PROF) { const long long now_ = clock64(); prof[slot] += now_ - tlast; tlast = now_; } } while (0)
 
     if (warp < kLoaderWarps) {
-        // ================================ A loaders (+ accumulator drain) ================================
+        // ================================ A loaders: shared memory -> registers -> tensor memory ================================
         const int set = warp >> 2;                        // k-blocks kb % 2 == set
         const int q = warp & 3;                           // TMEM lane quarter
         const int i = i0 + q * 32 + lane;                 // this thread's channel
-        const bool i_ok = i < p.I;
-        long long coloff = 0;                             // float offset of (kh, kw, c) inside a window
-        if (i_ok) {
-            const int kh = i / p.run, off = i - kh * p.run;
-            coloff = (long long)kh * p.Wb * p.Cb + off;
+        const bool i_ok = i < p.I;                        // whole 32-channel groups are valid or not (I % 32 == 0)
+        // where this warp's channel group sits inside an A stage: its run's base, the run's row pitch, the group's column
+        uint32_t a_off = 0u, a_pitch = 128u;
+        {
+            Tc3Seg seg[4];
+            const int nseg = tile_segments(i0, p.I, p.run, seg);
+            for (int t = 0; t < nseg; ++t)
+                if (q >= seg[t].g0 && q < seg[t].g0 + seg[t].ng) {
+                    a_off = (uint32_t)seg[t].g0 * kAGroupBytes + (uint32_t)(q - seg[t].g0) * 128u + (uint32_t)lane * 4u;
+                    a_pitch = (uint32_t)seg[t].ng * 128u;
+                }
         }
-        const float* src = p.big + coloff;
-        // box origin -> float offset of its first window origin; position q adds rel_off[q] (valid while n0 + rel_n[q] < batch)
-        auto box_base = [&](int x0, int y0, int n0) -> long long {
-            return (long long)n0 * p.big_img + ((long long)(2 * y0) * p.Wb + 2 * x0) * p.Cb;
-        };
-
-        // ---- drain state (all 8 warps drain: quarter q x column half `set`)
-        constexpr int HALF_COLS = BN / 2;
-        const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * HALF_COLS);
-        float acc[HALF_COLS];
-#pragma unroll
-        for (int c = 0; c < HALF_COLS; ++c) acc[c] = 0.f;
-        int drained = 0;
-        auto drain_cols = [&](uint32_t taddr) {
-#pragma unroll
-            for (int cc = 0; cc < HALF_COLS; cc += 16) {
-                float v[16];
-                tmem_ld16(taddr + (uint32_t)cc, v);
-#pragma unroll
-                for (int c = 0; c < 16; ++c) acc[cc + c] += v[c];
-            }
-        };
-        auto drain_one = [&]() {
-            const int b = drained & 1;
-            mbar_wait(&chunk_bar[b], (uint32_t)((drained >> 1) & 1));
-            tc_fence_after();
-            drain_cols(tmem_acc + (uint32_t)(b * 2 * BN));
-            drain_cols(tmem_acc + (uint32_t)(b * 2 * BN + BN));
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&drained_bar[b]);
-            ++drained;
-        };
-
-        long long prof[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64();
+        long long prof[4] = {0, 0, 0, 0}, tlast = clock64();
         const long long tstart = tlast;
-        const bool PROF = (p.debug & 16) != 0;
-#define TC3_PROF(slot) do { if (PROF) { const long long now_ = clock64(); prof[slot] += now_ - tlast; tlast = now_; } } while (0)
         for (int kb = set; kb < nkb; kb += 2) {
             const int s = kb % kStages;
-            TC3_PROF(5);
-            // chunks finished two k-block pairs ago are drained while this k-block's loads are in flight
-            int x0, y0, n0;
-            box_origin(kb_begin + kb, x0, y0, n0);
+            const int sa = kb % kAStages;
             float v[kKR];
-            {
-                const float* bp = src + box_base(x0, y0, n0);
-                const int nleft = p.batch - n0;
-#pragma unroll
-                for (int qq = 0; qq < kKR; ++qq) v[qq] = (i_ok && rel_n[qq] < nleft) ? __ldg(bp + rel_off[qq]) : 0.f;
-            }
+            // every warp waits (also one whose channel group lies past I): its arrival on a_free must not overtake the slot's phase
+            mbar_wait(&a_full[sa], (uint32_t)((kb / kAStages) & 1));
             TC3_PROF(0);
-            // L2 prefetch of the k-block kPrefetchKb ahead (one 128-byte line per position and warp)
-            if (kb + kPrefetchKb < nkb) {
-                int px, py, pn;
-                box_origin(kb_begin + kb + kPrefetchKb, px, py, pn);
-                const float* bp = src + box_base(px, py, pn);
-                const int nleft = p.batch - pn;
-#pragma unroll 8
-                for (int qq = 0; qq < kKR; ++qq)
-                    if (i_ok && rel_n[qq] < nleft) asm volatile("prefetch.global.L2 [%0];" ::"l"(bp + rel_off[qq]) : "memory");
+            if (i_ok) {
+                const uint32_t ap = a_base + (uint32_t)sa * kAStageBytes + a_off;
+#pragma unroll
+                for (int qq = 0; qq < kKR; ++qq) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[qq]) : "r"(ap + (uint32_t)qq * a_pitch));
+            } else {
+#pragma unroll
+                for (int qq = 0; qq < kKR; ++qq) v[qq] = 0.f;
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_free[sa]);       // the values are in registers: the copy engine may refill the slot
             TC3_PROF(1);
-            while (drained < kb / kChunkKb - 1) drain_one();
-            TC3_PROF(2);
             if (kb >= kStages) mbar_wait(&empty_bar[s], (uint32_t)((kb / kStages - 1) & 1));     // the MMAs that read this TMEM slot are done
-            TC3_PROF(3);
+            TC3_PROF(2);
             tc_fence_after();
             const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ACC_COLS + s * 64);
             tmem_st32(ta, v);                              // a_hi = raw values
@@ -233,45 +241,143 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap smallmap, const __grid_cons
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_ready[s]);
-            TC3_PROF(4);
+            TC3_PROF(3);
         }
-        if (PROF && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (warp == 0 || warp == 4))
-            printf("tc3prof warp %d nkb %d total %lld: issue_loads %lld prefetch %lld drain %lld wait_empty %lld wait_data+st %lld other %lld\n",
-                   warp, nkb, clock64() - tstart, prof[0], prof[1], prof[2], prof[3], prof[4], prof[5]);
-        while (drained < nchunks) drain_one();
-        // ---- partial[split][i][j]
-        if (i_ok) {
-            float* out = p.partial + ((long long)blockIdx.z * p.I + i) * p.J + j0 + set * HALF_COLS;
+        if (PROF && lane == 0 && (warp == 0 || warp == 4))
+            printf("tc3prof loader warp %d nkb %d total %lld: wait_a_full %lld lds %lld wait_empty %lld split+st %lld\n",
+                   warp, nkb, clock64() - tstart, prof[0], prof[1], prof[2], prof[3]);
+    } else if (warp >= kDrainWarp0) {
+        // ================================ accumulator drain (warps 12-15 = TMEM lane quarters 0-3) ================================
+        // Each finished 128-position chunk is added to fp32 register accumulators (the tensor core accumulates with
+        // round-toward-zero, see tc_tapgemm.cu); at the end every thread writes its row of partial[split][i][j0 .. j0 + BN).
+        const int q = warp & 3;
+        const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16);
+        float acc[BN];
 #pragma unroll
-            for (int c = 0; c < HALF_COLS; c += 4)
+        for (int c = 0; c < BN; ++c) acc[c] = 0.f;
+        // Between chunks these warps pull the operands of the k-blocks up to kPrefetchKb ahead of the producer into L2
+        // (prefetch.global.L2, one 128-byte line per lane and instruction; both operands stream from HBM exactly once).
+        // They never block on it: `progress` bounds how far ahead they may run, a finished chunk always comes first.
+        const int t = tid - kDrainWarp0 * 32;
+        constexpr int NT = kDrainWarps * 32;
+        constexpr int SLOTS = (kKR * (4 + NGB) + NT - 1) / NT;      // lines per lane and k-block
+        int ngroups = 0;
+        while (ngroups < 4 && i0 + 32 * ngroups < p.I) ++ngroups;
+        const int per_pos = ngroups + NGB;                          // A channel groups + B column groups: one line each per position
+        long long rel[SLOTS];                                       // float offset of the lane's line from the box origin of its tensor
+        int rel_n[SLOTS];                                           // image of the line relative to the box (-1: no line)
+        bool is_b[SLOTS];
+        {
+            const int bwh = p.bw * p.bh;
+#pragma unroll
+            for (int k = 0; k < SLOTS; ++k) {
+                const int l = t + k * NT;
+                rel_n[k] = -1; rel[k] = 0; is_b[k] = false;
+                if (l >= kKR * per_pos) continue;
+                const int pos = l / per_pos, g = l - pos * per_pos;
+                const int nn = pos / bwh, rr = pos - nn * bwh;
+                const int yy = rr / p.bw, xx = rr - yy * p.bw;
+                rel_n[k] = nn;
+                if (g < ngroups) {
+                    const int ig = i0 + 32 * g, kh = ig / p.run;
+                    rel[k] = (long long)nn * p.big_img + ((long long)(p.sx * yy + kh) * p.Wb + p.sx * xx) * p.Cb + (ig - kh * p.run);
+                } else {
+                    is_b[k] = true;
+                    rel[k] = (((long long)nn * p.Ho + yy) * p.Wo + xx) * p.J + j0 + 32 * (g - ngroups);
+                }
+            }
+        }
+        Cursor pc = cursor_at(kb_begin);
+        int pnext = (p.debug & 8) ? nkb : 0;                        // debug 8: no L2 prefetch
+        auto prefetch_some = [&]() -> bool {
+            if (pnext >= nkb || pnext >= *reinterpret_cast<volatile int*>(&progress) + kPrefetchKb) return false;
+            const int x0 = pc.tx * p.bw, y0 = pc.ty * p.bh, n0 = pc.tn * p.bn;
+            const long long a_org = (long long)n0 * p.big_img + ((long long)(p.sx * y0) * p.Wb + p.sx * x0) * p.Cb;
+            const long long b_org = (((long long)n0 * p.Ho + y0) * p.Wo + x0) * p.J;
+#pragma unroll
+            for (int k = 0; k < SLOTS; ++k) {
+                if (rel_n[k] < 0 || n0 + rel_n[k] >= p.batch) continue;
+                const float* a = is_b[k] ? p.small + b_org + rel[k] : p.big + a_org + rel[k];
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a) : "memory");
+            }
+            cursor_next(pc);
+            ++pnext;
+            return true;
+        };
+        auto chunk_done = [&](int b, uint32_t parity) -> bool {
+            uint32_t ok;
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok) : "r"(smem_u32(&chunk_bar[b])), "r"(parity) : "memory");
+            return __all_sync(0xffffffffu, ok != 0);
+        };
+        long long prof[4] = {0, 0, 0, 0}, tlast = clock64();
+        const long long tstart = tlast;
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int b = ch & 1;
+            while (!chunk_done(b, (uint32_t)((ch >> 1) & 1)))
+                if (!prefetch_some()) __nanosleep(64);
+            TC3_PROF(0);
+            tc_fence_after();
+#pragma unroll
+            for (int cc = 0; cc < BN; cc += 32) {
+                float v[16], w[16], x[16], y[16];
+                tmem_ld16_issue(tmem_acc + (uint32_t)(b * 2 * BN + cc), v);
+                tmem_ld16_issue(tmem_acc + (uint32_t)(b * 2 * BN + cc + 16), w);
+                tmem_ld16_issue(tmem_acc + (uint32_t)(b * 2 * BN + BN + cc), x);
+                tmem_ld16_issue(tmem_acc + (uint32_t)(b * 2 * BN + BN + cc + 16), y);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 16; ++c) { acc[cc + c] += v[c] + x[c]; acc[cc + 16 + c] += w[c] + y[c]; }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&drained_bar[b]);
+            TC3_PROF(1);
+        }
+        const int i = i0 + q * 32 + lane;
+        if (i < p.I) {
+            float* out = p.partial + ((long long)blockIdx.z * p.I + i) * p.J + j0;
+#pragma unroll
+            for (int c = 0; c < BN; c += 4)
                 *reinterpret_cast<float4*>(out + c) = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
         }
+        if (PROF && lane == 0 && warp == kDrainWarp0)
+            printf("tc3prof drain nkb %d total %lld: wait_chunk %lld drain %lld\n", nkb, clock64() - tstart, prof[0], prof[1]);
     } else if (warp == kProducerWarp) {
-        // ================================ B producer ================================
+        // ================================ producer: B boxes and A run boxes of every k-block ================================
         if (lane == 0 && nkb > 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&smallmap)) : "memory");
-            auto prefetch_b = [&](int kb) {
-                if (kb >= nkb) return;
-                int x0, y0, n0;
-                box_origin(kb_begin + kb, x0, y0, n0);
-#pragma unroll
-                for (int g = 0; g < NGB; ++g)
-                    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
-                                 ::"l"(reinterpret_cast<uint64_t>(&smallmap)), "r"(j0 + 32 * g), "r"(x0), "r"(y0), "r"(n0) : "memory");
-            };
-            for (int kb = 0; kb < kPrefetchKb; ++kb) prefetch_b(kb);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % kStages;
-                prefetch_b(kb + kPrefetchKb);
-                if (kb >= kStages) mbar_wait(&empty_bar[s], (uint32_t)((kb / kStages - 1) & 1));
-                const uint32_t stage = smem_base + (uint32_t)s * STAGE_BYTES;
-                mbar_expect_tx(&b_full[s], GROUP_BYTES * NGB);
-                int x0, y0, n0;
-                box_origin(kb_begin + kb, x0, y0, n0);
-#pragma unroll
-                for (int g = 0; g < NGB; ++g)
-                    tma_load_4d(stage + (uint32_t)g * GROUP_BYTES, &smallmap, j0 + 32 * g, x0, y0, n0, &b_full[s]);
+            Tc3Seg seg[4];
+            const int nseg = tile_segments(i0, p.I, p.run, seg);
+            uint32_t tx = 0;
+            for (int t = 0; t < nseg; ++t) {
+                asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&bigmaps.m[seg[t].ng - 1])) : "memory");
+                tx += (uint32_t)seg[t].ng * kAGroupBytes;
             }
+            Cursor c = cursor_at(kb_begin);
+            long long prof[4] = {0, 0, 0, 0}, tlast = clock64();
+            const long long tstart = tlast;
+            for (int kb = 0; kb < nkb; ++kb, cursor_next(c)) {
+                const int sb = kb % kBStages, sa = kb % kAStages;
+                const int x0 = c.tx * p.bw, y0 = c.ty * p.bh, n0 = c.tn * p.bn;
+                if (kb >= kBStages) mbar_wait(&b_empty[sb], (uint32_t)((kb / kBStages - 1) & 1));
+                *reinterpret_cast<volatile int*>(&progress) = kb;
+                TC3_PROF(0);
+                mbar_expect_tx(&b_full[sb], GROUP_BYTES * NGB);
+#pragma unroll
+                for (int g = 0; g < NGB; ++g)
+                    tma_load_4d(smem_base + (uint32_t)sb * STAGE_BYTES + (uint32_t)g * GROUP_BYTES, &smallmap, j0 + 32 * g, x0, y0, n0, &b_full[sb]);
+                TC3_PROF(2);
+                if (kb >= kAStages) mbar_wait(&a_free[sa], (uint32_t)((kb / kAStages - 1) & 1));
+                TC3_PROF(1);
+                mbar_expect_tx(&a_full[sa], tx);
+                for (int t = 0; t < nseg; ++t)
+                    tma_load_4d(a_base + (uint32_t)sa * kAStageBytes + (uint32_t)seg[t].g0 * kAGroupBytes, &bigmaps.m[seg[t].ng - 1], seg[t].off0, x0, p.sx * y0 + seg[t].kh,
+                                n0, &a_full[sa]);
+                TC3_PROF(2);
+            }
+            *reinterpret_cast<volatile int*>(&progress) = nkb;
+            if (PROF) printf("tc3prof producer nkb %d total %lld: wait_b_empty %lld wait_a_free %lld issue %lld\n", nkb, clock64() - tstart, prof[0], prof[1], prof[2]);
         }
         __syncwarp();
     } else if (warp >= kSplitWarp0 && warp < kSplitWarp0 + kSplitWarps) {
@@ -279,9 +385,9 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap smallmap, const __grid_cons
         const int tl = tid - kSplitWarp0 * 32;
         constexpr uint32_t CHUNKS = NGB * GROUP_BYTES / 16;
         for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % kStages;
-            mbar_wait(&b_full[s], (uint32_t)((kb / kStages) & 1));
-            const uint32_t stage = smem_base + (uint32_t)s * STAGE_BYTES;
+            const int sb = kb % kBStages;
+            mbar_wait(&b_full[sb], (uint32_t)((kb / kBStages) & 1));
+            const uint32_t stage = smem_base + (uint32_t)sb * STAGE_BYTES;
 #pragma unroll 4
             for (uint32_t c = (uint32_t)tl; c < CHUNKS; c += kSplitWarps * 32) {
                 const uint32_t a = stage + c * 16u;
@@ -292,7 +398,7 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap smallmap, const __grid_cons
             }
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&b_ready[s]);
+            if (lane == 0) mbar_arrive(&b_ready[sb]);
         }
     } else if (warp == kIssuerWarp) {
         // ================================ MMA issuer ================================
@@ -301,15 +407,20 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap smallmap, const __grid_cons
             const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(TBM >> 4) << 24);
             const uint32_t idesc = idesc_base | ((uint32_t)(BN >> 3) << 17);
             const uint32_t idesc2 = idesc_base | ((uint32_t)((2 * BN) >> 3) << 17);
+            long long prof[4] = {0, 0, 0, 0}, tlast = clock64();
+            const long long tstart = tlast;
             for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t stage = smem_base + (uint32_t)s * STAGE_BYTES;
+                const int s = kb % kStages, sb = kb % kBStages;
+                const uint32_t stage = smem_base + (uint32_t)sb * STAGE_BYTES;
                 const int chunk = kb / kChunkKb;
                 const int b = chunk & 1;
-                const uint32_t par = (uint32_t)((kb / kStages) & 1);
-                mbar_wait(&a_ready[s], par);
-                mbar_wait(&b_ready[s], par);
+                TC3_PROF(3);
+                mbar_wait(&b_ready[sb], (uint32_t)((kb / kBStages) & 1));
+                TC3_PROF(0);
+                mbar_wait(&a_ready[s], (uint32_t)((kb / kStages) & 1));
+                TC3_PROF(1);
                 if (kb % kChunkKb == 0 && chunk >= 2) mbar_wait(&drained_bar[b], (uint32_t)(((chunk >> 1) - 1) & 1));
+                TC3_PROF(2);
                 tc_fence_after();
                 const uint32_t d_main = tmem_base + (uint32_t)(b * 2 * BN);
                 const uint32_t d_cross = d_main + (uint32_t)BN;
@@ -321,8 +432,11 @@ tc3_wgrad_kernel(const __grid_constant__ CUtensorMap smallmap, const __grid_cons
                     umma_tf32_ts(d_cross, ta + 32u + (uint32_t)(ks * 8), b_hi, idesc, 1u);
                 }
                 umma_commit(&empty_bar[s]);
+                umma_commit(&b_empty[sb]);
                 if (kb % kChunkKb == kChunkKb - 1 || kb == nkb - 1) umma_commit(&chunk_bar[b]);
             }
+            if (PROF)
+                printf("tc3prof issuer nkb %d total %lld: wait_b_ready %lld wait_a_ready %lld wait_drained %lld issue+other %lld\n", nkb, clock64() - tstart, prof[0], prof[1], prof[2], prof[3]);
         }
         __syncwarp();
     }
@@ -346,10 +460,10 @@ bool pick_box32(int gw, int gh, int& bw, int& bh, int& bn) {
 }
 
 template <int BN>
-int32_t launch_bn(const CUtensorMap& smallmap, const Tc3WgParams& p, int splits, cudaStream_t stream) {
-    const size_t smem = (size_t)kKR * 128 * 2 * (BN / 32) * kStages + 1024;
+int32_t launch_bn(const CUtensorMap& smallmap, const Tc3BigMaps& bigmaps, const Tc3WgParams& p, int splits, cudaStream_t stream) {
+    const size_t smem = (size_t)kKR * 128 * 2 * (BN / 32) * kBStages + (size_t)kAStageBytes * kAStages + 1024;
     dim3 grid((unsigned)cdiv(p.I, TBM), (unsigned)(p.J / BN), (unsigned)splits);
-    tc3_wgrad_kernel<BN><<<grid, kThreads, smem, stream>>>(smallmap, p);
+    tc3_wgrad_kernel<BN><<<grid, kThreads, smem, stream>>>(smallmap, bigmaps, p);
     CPB_LAUNCHED();
     return CPB_OK;
 }
@@ -367,8 +481,8 @@ int32_t tc3_wgrad_init() {
     const char* e = getenv("CPB_TC3_WGRAD");
     g_tc3_enabled = e ? atoi(e) : 0;
     g_tc3_probe = 1;
-    CPB_CUDA(cudaFuncSetAttribute(tc3_wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024 + 1024));
-    CPB_CUDA(cudaFuncSetAttribute(tc3_wgrad_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024 + 1024));
+    CPB_CUDA(cudaFuncSetAttribute(tc3_wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024 + 1024));
+    CPB_CUDA(cudaFuncSetAttribute(tc3_wgrad_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024 + 1024));
     return CPB_OK;
 }
 
@@ -403,6 +517,7 @@ int32_t launch_tc3_wgrad(const WgradParams& w, cudaStream_t stream) {
     p.big = w.big; p.I = w.I; p.J = w.J; p.batch = w.batch;
     p.Cb = w.big_pitch; p.run = w.run; p.Wb = dense ? 0 : w.Wb; p.big_img = w.big_img;
     p.partial = w.partial;
+    p.small = w.small; p.Wo = dense ? 1 : w.Wo; p.Ho = dense ? 1 : w.Ho;
     p.debug = w.tc_variant;
     alignas(64) CUtensorMap smallmap;
     const unsigned long long dims[4] = {(unsigned long long)w.J, (unsigned long long)w.Wo, (unsigned long long)w.Ho, (unsigned long long)w.batch};
@@ -410,7 +525,40 @@ int32_t launch_tc3_wgrad(const WgradParams& w, cudaStream_t stream) {
     const unsigned box[4] = {32u, (unsigned)p.bw, (unsigned)p.bh, (unsigned)p.bn};
     const unsigned estr[4] = {1u, 1u, 1u, 1u};
     CPB_TRY(tc2_encode_tiled(&smallmap, w.small, 4, dims, strides, box, estr, 1));
-    return w.J == 64 ? launch_bn<64>(smallmap, p, w.splits, stream) : launch_bn<32>(smallmap, p, w.splits, stream);
+    // big as a tensor of WINDOW RUNS {f, x, row, image}: f = float inside the kernel row's run starting at window origin x
+    // (stride 2 pixels -- consecutive windows overlap, which the tensor map does not mind), rows traversed with stride 2.
+    // A box = the 32 window origins of a k-block x (32 w) contiguous floats, unswizzled; one map per box width w.
+    Tc3BigMaps bigmaps;
+    memset(&bigmaps, 0, sizeof(bigmaps));
+    p.sx = dense ? 1 : 2;
+    {
+        const unsigned long long pitch = (unsigned long long)w.big_pitch;
+        const unsigned long long Wb = dense ? 1ull : (unsigned long long)w.Wb;
+        const unsigned long long Hb = dense ? 1ull : (unsigned long long)(w.big_img / ((long long)w.Wb * w.big_pitch));
+        const unsigned long long xs = dense ? 1ull : (unsigned long long)w.Wo;
+        const unsigned long long f_extent = dense ? (unsigned long long)w.I : (Wb - 2ull * (xs - 1ull)) * pitch;       // floats a window may span in its row
+        CPB_REQUIRE(f_extent >= (unsigned long long)w.run, "tc3_wgrad: window run leaves the image row");
+        const unsigned long long bdims[4] = {f_extent, xs, Hb, (unsigned long long)w.batch};
+        const unsigned long long bstrides[3] = {(dense ? pitch : 2ull * pitch) * 4ull, Wb * pitch * 4ull, (unsigned long long)w.big_img * 4ull};
+        const unsigned es = (unsigned)p.sx;
+        const unsigned bestr[4] = {1u, 1u, es, 1u};
+        bool need[4] = {false, false, false, false};
+        for (int i0 = 0; i0 < w.I; i0 += TBM) {
+            int prev_kh = -1, ng = 0;
+            for (int g = 0; g < 4 && i0 + 32 * g < w.I; ++g) {
+                const int kh = (i0 + 32 * g) / w.run;
+                if (kh != prev_kh && ng > 0) { need[ng - 1] = true; ng = 0; }
+                prev_kh = kh; ++ng;
+            }
+            if (ng > 0) need[ng - 1] = true;
+        }
+        for (int wd = 1; wd <= 4; ++wd) {
+            if (!need[wd - 1]) continue;
+            const unsigned bbox[4] = {32u * (unsigned)wd, (unsigned)p.bw, (unsigned)p.bh * es, (unsigned)p.bn};
+            CPB_TRY(tc2_encode_tiled(&bigmaps.m[wd - 1], w.big, 4, bdims, bstrides, bbox, bestr, 2));
+        }
+    }
+    return w.J == 64 ? launch_bn<64>(smallmap, bigmaps, p, w.splits, stream) : launch_bn<32>(smallmap, bigmaps, p, w.splits, stream);
 }
 
 }  // namespace cpb

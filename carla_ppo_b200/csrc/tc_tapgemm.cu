@@ -583,8 +583,15 @@ __global__ void tc_weights_kernel(const float* __restrict__ params, float* __res
     const int nn = n % BN, cc = c % TBK;
     if (job.raw) {      // tc2 block order (n-tile, tap, k-block); each block = [hi image | lo image]
         const long long block = ((long long)(n / BN) * job.ntaps + tap) * (job.C / TBK) + c / TBK;
-        const long long at2 = job.dst_hi + block * (2 * BN * TBK) + (nn >> 3) * 256 + (nn & 7) * 32 + ((((cc >> 2) ^ (nn & 7))) << 2) + (cc & 3);
         const float hi2 = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+        if (job.raw == 2) {     // CTA-pair order: CTA r of the pair copies [hi rows r*h .. | lo rows r*h ..], h = BN/2
+            const int h = BN / 2, r = nn / h, nl = nn - r * h;
+            const long long at3 = job.dst_hi + block * (2 * BN * TBK) + (long long)r * (2 * h * TBK) + (nl >> 3) * 256 + (nl & 7) * 32 + ((((cc >> 2) ^ (nl & 7))) << 2) + (cc & 3);
+            dst[at3] = hi2;
+            dst[at3 + h * TBK] = x - hi2;
+            return;
+        }
+        const long long at2 = job.dst_hi + block * (2 * BN * TBK) + (nn >> 3) * 256 + (nn & 7) * 32 + ((((cc >> 2) ^ (nn & 7))) << 2) + (cc & 3);
         dst[at2] = hi2;
         dst[at2 + BN * TBK] = x - hi2;
         return;

@@ -505,14 +505,14 @@ static int32_t relayout_weights(const VaePlan& pl, const VaeLayout& L, const flo
             TcWeightJob& j = w.jobs[w.njobs++];
             j.src_off = L.off[tensor]; j.dst_hi = pl.rl.tc[slot].f_hi; j.dst_lo = pl.rl.tc[slot].f_lo;
             j.mode = 1; j.k = k; j.cb = cb; j.cs = cs; j.N = cs; j.C = k * cb; j.count = n; w.total += n;
-            j.raw = tc2_enabled() ? 1 : 0; j.ntaps = k;
+            j.raw = tc2_enabled() ? tc2_weight_layout() : 0; j.ntaps = k;
         }
         if (scatter) {
             TcWeightJob& j = w.jobs[w.njobs++];
             j.src_off = L.off[tensor]; j.dst_hi = pl.rl.tc[slot].t_hi; j.dst_lo = pl.rl.tc[slot].t_lo;
             const int win = (k + 1) / 2;
             j.mode = 2; j.k = k; j.cb = cb; j.cs = cs; j.N = 4 * cb; j.C = cs; j.count = (long long)win * win * 4 * cb * cs; w.total += j.count;
-            j.raw = tc2_enabled() ? 1 : 0; j.ntaps = win * win;
+            j.raw = tc2_enabled() ? tc2_weight_layout() : 0; j.ntaps = win * win;
         }
     };
     // conv layers run gather-form forward / scatter-form dgrad; deconv layers the other way round
@@ -924,7 +924,7 @@ int32_t cpb_debug_tc_gemm(const float* a, const float* bt, float* d, int32_t m, 
     p.wk_hi = scratch; p.wk_lo = scratch + (long long)n * k;
     p.debug = tc_debug_flags();
     const bool use_tc2 = tc2_tapgemm_supported(p, 0);
-    w.jobs[0].raw = use_tc2 ? 1 : 0; w.jobs[0].ntaps = 1;
+    w.jobs[0].raw = use_tc2 ? tc2_weight_layout() : 0; w.jobs[0].ntaps = 1;
     CPB_TRY(launch_tc_weights(bt, scratch, w, s));
     if (use_tc2) return launch_tc2_tapgemm(p, 0, s);
     float* lo = scratch + 2LL * n * k;
