@@ -203,11 +203,14 @@ __device__ __forceinline__ void loss_elem(float x, float y, float& val, float& d
 template <int LOSS, int CT>
 __global__ void __launch_bounds__(256)
 recon_loss_kernel(const float4* logits_p, const float4* __restrict__ target_p, int npix, float gscale,
-                  float* __restrict__ frame_loss, float4* dlogits_p) {
+                  float* __restrict__ frame_loss, float4* dlogits_p, float* __restrict__ frame_dsum) {
     // logits_p and dlogits_p MAY ALIAS (the training path overwrites the logits with d loss / d logits in place): neither
     // is __restrict__, each element is read before it is written by the same thread.
+    // frame_dsum (optional): [batch][4] per-frame channel sums of d loss / d logits -- the last layer's bias gradient is their
+    // column sum, which saves a separate pass over the [B, 80, 160, 4] gradient image
     const long long base = (long long)blockIdx.x * npix;
     float sum = 0.f;
+    float ds[4] = {0.f, 0.f, 0.f, 0.f};
     for (int p = threadIdx.x; p < npix; p += blockDim.x) {
         const float4 l = logits_p[base + p];
         const float4 y = target_p[base + p];
@@ -220,17 +223,27 @@ recon_loss_kernel(const float4* logits_p, const float4* __restrict__ target_p, i
             loss_elem<LOSS>(lv[c], yv[c], val, dx);
             sum += val;
             d[c] = dx * gscale;
+            ds[c] += d[c];
         }
         if (dlogits_p != nullptr) dlogits_p[base + p] = make_float4(d[0], d[1], d[2], d[3]);
     }
-    __shared__ float red[8];
+    __shared__ float red[5][8];
     sum = warp_sum(sum);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    if (frame_dsum != nullptr) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) ds[c] = warp_sum(ds[c]);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = sum;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) red[1 + c][threadIdx.x >> 5] = ds[c];
+    }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 5 && (threadIdx.x == 0 || frame_dsum != nullptr)) {
         float t = 0.f;
-        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
-        frame_loss[blockIdx.x] = t;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[threadIdx.x][i];
+        if (threadIdx.x == 0) frame_loss[blockIdx.x] = t;
+        else frame_dsum[(long long)blockIdx.x * 4 + threadIdx.x - 1] = t;
     }
 }
 
@@ -324,6 +337,19 @@ __global__ void colsum_final_kernel(const float* __restrict__ partial, int nbloc
     if (c >= c_real) return;
     float s = 0.f;
     for (int b = lane; b < nblocks; b += 32) s += partial[(long long)b * pitch + c];
+    s = warp_sum(s);
+    if (lane == 0) out[c] = s;
+}
+
+// Column sums produced by a tap-GEMM epilogue (TapGemmParams::colsum): out[c] = sum over the `rows` (CTA, quarter) rows and
+// the N / cb parity classes of partial[row][class * cb + c].  One warp per channel, fixed order.
+__global__ void colsum_fold_kernel(const float* __restrict__ partial, int rows, int N, int cb, float* __restrict__ out) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= cb) return;
+    float s = 0.f;
+    for (int r = lane; r < rows; r += 32)
+        for (int k = c; k < N; k += cb) s += partial[(long long)r * N + k];
     s = warp_sum(s);
     if (lane == 0) out[c] = s;
 }
@@ -444,26 +470,26 @@ int32_t launch_reparam_bwd(const float* heads, const float* eps, const float* gz
 
 template <int LOSS>
 static int32_t launch_recon_loss_t(const float* logits_p, const float* target_p, int batch, int ct, float gscale,
-                                   float* frame_loss, float* dlogits_p, cudaStream_t stream) {
+                                   float* frame_loss, float* dlogits_p, float* frame_dsum, cudaStream_t stream) {
     const int npix = 80 * 160;
     if (ct == 3)
         recon_loss_kernel<LOSS, 3><<<batch, 256, 0, stream>>>((const float4*)logits_p, (const float4*)target_p, npix,
-                                                              gscale, frame_loss, (float4*)dlogits_p);
+                                                              gscale, frame_loss, (float4*)dlogits_p, frame_dsum);
     else
         recon_loss_kernel<LOSS, 1><<<batch, 256, 0, stream>>>((const float4*)logits_p, (const float4*)target_p, npix,
-                                                              gscale, frame_loss, (float4*)dlogits_p);
+                                                              gscale, frame_loss, (float4*)dlogits_p, frame_dsum);
     CPB_LAUNCHED();
     return CPB_OK;
 }
 
 int32_t launch_recon_loss(const float* logits_p, const float* target_p, int batch, int ct, int loss_type,
-                          float gscale, float* frame_loss, float* dlogits_p, cudaStream_t stream) {
+                          float gscale, float* frame_loss, float* dlogits_p, cudaStream_t stream, float* frame_dsum) {
     CPB_REQUIRE(ct == 1 || ct == 3, "recon_loss: target_channels must be 1 or 3");
     if (batch == 0) return CPB_OK;
     switch (loss_type) {
-        case CPB_LOSS_MSE: return launch_recon_loss_t<CPB_LOSS_MSE>(logits_p, target_p, batch, ct, gscale, frame_loss, dlogits_p, stream);
-        case CPB_LOSS_BCE: return launch_recon_loss_t<CPB_LOSS_BCE>(logits_p, target_p, batch, ct, gscale, frame_loss, dlogits_p, stream);
-        case CPB_LOSS_BCE_V2: return launch_recon_loss_t<CPB_LOSS_BCE_V2>(logits_p, target_p, batch, ct, gscale, frame_loss, dlogits_p, stream);
+        case CPB_LOSS_MSE: return launch_recon_loss_t<CPB_LOSS_MSE>(logits_p, target_p, batch, ct, gscale, frame_loss, dlogits_p, frame_dsum, stream);
+        case CPB_LOSS_BCE: return launch_recon_loss_t<CPB_LOSS_BCE>(logits_p, target_p, batch, ct, gscale, frame_loss, dlogits_p, frame_dsum, stream);
+        case CPB_LOSS_BCE_V2: return launch_recon_loss_t<CPB_LOSS_BCE_V2>(logits_p, target_p, batch, ct, gscale, frame_loss, dlogits_p, frame_dsum, stream);
     }
     CPB_REQUIRE(false, "recon_loss: unknown loss_type %d", loss_type);
 }
@@ -492,9 +518,9 @@ int32_t launch_recon_loss_flat(const float* logits, const float* target, int bat
     if (batch == 0) return CPB_OK;
     const int n4 = n / 4;
     switch (loss_type) {
-        case CPB_LOSS_MSE: recon_loss_kernel<CPB_LOSS_MSE, 4><<<batch, 256, 0, stream>>>((const float4*)logits, (const float4*)target, n4, gscale, frame_loss, (float4*)dlogits); break;
-        case CPB_LOSS_BCE: recon_loss_kernel<CPB_LOSS_BCE, 4><<<batch, 256, 0, stream>>>((const float4*)logits, (const float4*)target, n4, gscale, frame_loss, (float4*)dlogits); break;
-        case CPB_LOSS_BCE_V2: recon_loss_kernel<CPB_LOSS_BCE_V2, 4><<<batch, 256, 0, stream>>>((const float4*)logits, (const float4*)target, n4, gscale, frame_loss, (float4*)dlogits); break;
+        case CPB_LOSS_MSE: recon_loss_kernel<CPB_LOSS_MSE, 4><<<batch, 256, 0, stream>>>((const float4*)logits, (const float4*)target, n4, gscale, frame_loss, (float4*)dlogits, nullptr); break;
+        case CPB_LOSS_BCE: recon_loss_kernel<CPB_LOSS_BCE, 4><<<batch, 256, 0, stream>>>((const float4*)logits, (const float4*)target, n4, gscale, frame_loss, (float4*)dlogits, nullptr); break;
+        case CPB_LOSS_BCE_V2: recon_loss_kernel<CPB_LOSS_BCE_V2, 4><<<batch, 256, 0, stream>>>((const float4*)logits, (const float4*)target, n4, gscale, frame_loss, (float4*)dlogits, nullptr); break;
         default: CPB_REQUIRE(false, "recon_loss_flat: unknown loss_type %d", loss_type);
     }
     CPB_LAUNCHED();
@@ -510,6 +536,14 @@ int32_t launch_finalize_losses(const float* frame_loss, const float* kl_rows, in
 
 long long colsum_scratch_floats(long long rows, int pitch) {
     return colsum_blocks(rows, pitch) * pitch;
+}
+
+int32_t launch_colsum_fold(const float* partial, int rows, int N, int cb, float* out, cudaStream_t stream) {
+    CPB_REQUIRE(cb > 0 && N % cb == 0, "colsum_fold: N must be a multiple of the channel count");
+    ProfScope prof("bias_grad.colsum", stream);
+    colsum_fold_kernel<<<cdiv(cb, 8), 256, 0, stream>>>(partial, rows, N, cb, out);
+    CPB_LAUNCHED();
+    return CPB_OK;
 }
 
 int32_t launch_colsum(const float* g, long long rows, int pitch, int c_real, float* out, float* scratch,

@@ -18,8 +18,10 @@ int32_t launch_deconv4_fwd(const float* small, const float* w /*[4,4,Ct,32]*/, c
 // 3-channel edge layers (edge.cu): big4 = float4-per-pixel padded image [B,80,160,4], small [B,39,79,32], w = TF kernel [4,4,cb,32]
 // gather: conv1 forward (mask == nullptr: bias + ReLU) / deconv4 data-gradient (mask != nullptr: ReLU mask, no bias)
 // small_lo (nullable): also write small - trunc_tf32(small), the second TF32 operand of the tensor-core consumer
+// cs_partial (optional, mask form only): [edge_gather_blocks(batch)][32] per-CTA column sums of `small` (bias gradient)
 int32_t launch_edge_gather(const float* big4, int cb, const float* w, const float* bias, const float* mask,
-                           float* small, float* small_lo, int batch, cudaStream_t stream);
+                           float* small, float* small_lo, int batch, cudaStream_t stream, float* cs_partial = nullptr);
+long long edge_gather_blocks(int batch);
 // weight gradient: partial[edge_wgrad_ctas(batch)][16*cb][32]; reduce with launch_reduce_partials
 int edge_wgrad_ctas(int batch);
 int32_t launch_edge_wgrad(const float* big4, int cb, const float* small, int batch, float* partial, cudaStream_t stream);
@@ -34,8 +36,9 @@ int32_t launch_reparam_bwd(const float* heads, const float* eps, const float* gz
                            int batch, int zdim, float coef, float* gheads, cudaStream_t stream);
 
 // logits_p, target_p [B,12800,4] -> frame_loss [B]; dlogits_p [B,12800,4] (nullable) = gscale * dl/dx
+// frame_dsum (optional): [batch][4] per-frame channel sums of the gradient image (column-summed later = last layer's bias gradient)
 int32_t launch_recon_loss(const float* logits_p, const float* target_p, int batch, int ct, int loss_type,
-                          float gscale, float* frame_loss, float* dlogits_p, cudaStream_t stream);
+                          float gscale, float* frame_loss, float* dlogits_p, cudaStream_t stream, float* frame_dsum = nullptr);
 
 // MlpVAE (flattened frames, no channel padding): dst[i] = src[i] * scale with the verify_range flag; y = sigmoid(x);
 // reconstruction loss on unpadded [B, n] rows
@@ -50,6 +53,8 @@ int32_t launch_finalize_losses(const float* frame_loss, const float* kl_rows, in
 
 // out[c] = sum_r g[r*pitch + c]  for c < c_real   (deterministic two-pass; scratch >= colsum_scratch_floats)
 long long colsum_scratch_floats(long long rows, int pitch);
+// folds the (CTA, quarter) rows a tap-GEMM epilogue accumulated (TapGemmParams::colsum) into out[0:cb]
+int32_t launch_colsum_fold(const float* partial, int rows, int N, int cb, float* out, cudaStream_t stream);
 int32_t launch_colsum(const float* g, long long rows, int pitch, int c_real, float* out, float* scratch,
                       cudaStream_t stream);
 

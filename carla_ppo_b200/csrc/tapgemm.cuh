@@ -69,6 +69,9 @@ struct TapGemmParams {
     int quad_cb;
     int quad_lcb;         // log2(quad_cb), set by the launcher
     int cluster;          // tensor-core path: CTAs per cluster (set by the launcher)
+    float* colsum;        // tc2 path only: if set, the epilogue adds the column sums of what it stores (= the bias gradient of the layer
+                          // whose pre-activation gradient dst is) into colsum[(cta * 4 + lane quarter) * N + column]; the caller
+                          // zeroes the kTc2ColsumRows x N buffer before and folds it with launch_colsum_fold afterwards
     int debug;            // tensor-core path: timing decomposition (CPB_TC_DEBUG): 1 no MMA, 2 no A copies, 4 A copies zero-fill only, 8 no weight copies, 16 cycle accounting
     TapClass cls[4];
 };

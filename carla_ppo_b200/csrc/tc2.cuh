@@ -26,6 +26,7 @@
 
 namespace cpb {
 
+constexpr int kTc2ColsumRows = 4 * 160;   // (CTA, lane quarter) rows of a column-sum buffer: the persistent grid never exceeds 160 CTAs
 constexpr int kTc2MaxKb = 160;   // k-blocks per tile (conv4 / deconv1: 4 taps x 512 / 32 = 64; deconv3 quad: 9 x 2)
 
 struct Tc2KBlock {
@@ -49,6 +50,7 @@ struct Tc2Params {
     int quad, quad_cb, quad_lcb;
     int Hd, Wd, dst_pitch;
     long long dst_img;
+    float* colsum;               // see TapGemmParams::colsum
     int cluster;
     int debug;
     Tc2KBlock kb[kTc2MaxKb];

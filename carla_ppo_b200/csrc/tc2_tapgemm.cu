@@ -476,6 +476,7 @@ tc2_tapgemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
                 if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + ch0 + c_lane * 4));
                 constexpr int NIT = 32 / RPI;
                 constexpr int GB = 4;                 // rows in flight per lane (mask loads of a batch are issued together)
+                float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);      // column sums of this lane's rows (bias gradient)
 #pragma unroll
                 for (int i0 = 0; i0 < NIT; i0 += GB) {
                     float4 v[GB], mk[GB];
@@ -504,6 +505,24 @@ tc2_tapgemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
                             o.z = mk[u].z > 0.f ? o.z : 0.f; o.w = mk[u].w > 0.f ? o.w : 0.f;
                         }
                         *reinterpret_cast<float4*>(p.dst + offs[u]) = o;
+                        bs.x += o.x; bs.y += o.y; bs.z += o.z; bs.w += o.w;
+                    }
+                }
+                if (p.colsum != nullptr) {
+                    // fold the row groups (lanes with equal c_lane), then the lanes of row group 0 add their 4 columns to this
+                    // (CTA, quarter) row of the buffer.  Each address has ONE writer (this warp), its tiles come in a fixed
+                    // order and red.add never returns a value: deterministic, and no round trip is exposed.
+#pragma unroll
+                    for (int m = CPR; m < 32; m <<= 1) {
+                        bs.x += __shfl_xor_sync(0xffffffffu, bs.x, m); bs.y += __shfl_xor_sync(0xffffffffu, bs.y, m);
+                        bs.z += __shfl_xor_sync(0xffffffffu, bs.z, m); bs.w += __shfl_xor_sync(0xffffffffu, bs.w, m);
+                    }
+                    if (r_lane == 0) {
+                        float* cp = p.colsum + (size_t)(blockIdx.x * 4 + q) * p.N + st_y(st) * BN + half * HALF_COLS + sl * SLICE + c_lane * 4;
+                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(cp), "f"(bs.x) : "memory");
+                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(cp + 1), "f"(bs.y) : "memory");
+                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(cp + 2), "f"(bs.z) : "memory");
+                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(cp + 3), "f"(bs.w) : "memory");
                     }
                 }
                 __syncwarp();          // the next slice reuses the transposition tile
@@ -606,6 +625,7 @@ int32_t launch_bn(const CUtensorMap& map, Tc2Params& p, cudaStream_t stream) {
     const int resident = g_resident[bn_slot(BN)];
     CPB_REQUIRE(total_st < (1ll << 30) && resident > 0, "tc2_tapgemm: bad tile count");
     const unsigned grid = (unsigned)((total_st < resident ? total_st : resident) * p.cluster);
+    CPB_REQUIRE(p.colsum == nullptr || grid * 4 <= (unsigned)kTc2ColsumRows, "tc2_tapgemm: grid of %u CTAs exceeds the column-sum buffer", grid);
     if (g_pair) {
         if (p.debug & 16) return launch_t<BN, true, true>(map, p, (int)mtiles, (int)total_st, grid, stream);
         return launch_t<BN, true, false>(map, p, (int)mtiles, (int)total_st, grid, stream);
@@ -730,6 +750,7 @@ int32_t launch_tc2_tapgemm(const TapGemmParams& p, int scatter_k, cudaStream_t s
     q.tiles_n = (q.batch + q.bn - 1) / q.bn;
     q.N = p.N; q.wk = p.wk_hi;
     q.bias = p.bias; q.mask = p.mask; q.dst = p.dst; q.relu = p.relu;
+    q.colsum = p.colsum;
     q.quad = p.quad; q.quad_cb = p.quad_cb;
     if (p.quad) {
         CPB_REQUIRE((p.quad_cb & (p.quad_cb - 1)) == 0, "tc2_tapgemm: quad form needs a power-of-two channel count");

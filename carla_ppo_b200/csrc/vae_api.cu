@@ -179,12 +179,17 @@ static Relayout make_relayout(int z) {
     return r;
 }
 
+constexpr long long kColsumPartialFloats = (long long)kTc2ColsumRows * 512;      // column-sum rows of the widest layer (N = 512)
+
 struct VaePlan {
     int B, ct, z, mode;
     Relayout rl;
     float *relayout, *xp, *yp, *a1, *a2, *a3, *a4, *heads, *zbuf, *kl_rows, *kl_active, *frame_loss;
     float *d1, *b1, *b2, *b3, *logits_p;
     float *gA, *gB, *gz, *gheads, *partial, *colsum;
+    float* cs_partial;  // (CTA, quarter) x N column sums written by the tc2 tap-GEMM epilogues (bias gradients)
+    float* cs_edge;     // per-CTA column sums of deconv4's data gradient (edge_gather), [edge_gather_blocks(B)][32]
+    float* frame_dsum;  // per-frame channel sums of d loss / d logits, [B][4]
     float* lo;          // lo plane scratch for tensor-core sources whose producer does not write one (small tensors)
     float *a1_lo, *a2_lo, *a3_lo, *b1_lo, *b2_lo, *gA_lo, *gB_lo;   // lo planes written by the producing kernels
     float* ksplit;      // partial results of the k-split dense layers: kMaxKSplit x [2, B, z]
@@ -234,9 +239,14 @@ static VaePlan make_plan(void* ws, int64_t ws_bytes, int B, int ct, int z, int m
     p.heads = a.take<float>(2 * b * z);
     p.lo = a.take<float>(b * FEAT);
     p.ksplit = a.take<float>((int64_t)kMaxKSplit * 2 * b * z);
-    p.a1_lo = a.take<float>(b * H1 * W1 * C1);
-    p.a2_lo = a.take<float>(b * H2 * W2 * C2);
-    p.a3_lo = a.take<float>(b * H3 * W3 * C3);
+    // lo planes (x - trunc_tf32(x)) exist only for the round-1 tensor-core kernels (CPB_TC2=0): the tc2 kernels derive them in
+    // shared memory.  (A size query made before the library initialised on a device still counts them: conservative.)
+    const bool need_lo = !tc2_enabled();
+    if (need_lo) {
+        p.a1_lo = a.take<float>(b * H1 * W1 * C1);
+        p.a2_lo = a.take<float>(b * H2 * W2 * C2);
+        p.a3_lo = a.take<float>(b * H3 * W3 * C3);
+    }
     if (mode >= CPB_WS_FORWARD) {
         p.yp = a.take<float>(b * NPIX * 4);
         p.zbuf = a.take<float>(b * z);
@@ -245,8 +255,10 @@ static VaePlan make_plan(void* ws, int64_t ws_bytes, int B, int ct, int z, int m
         p.frame_loss = a.take<float>(b);
         p.d1 = a.take<float>(b * FEAT);
         p.b1 = a.take<float>(b * H3 * W3 * C3);
-        p.b1_lo = a.take<float>(b * H3 * W3 * C3);
-        p.b2_lo = a.take<float>(b * H2 * W2 * C2);
+        if (need_lo) {
+            p.b1_lo = a.take<float>(b * H3 * W3 * C3);
+            p.b2_lo = a.take<float>(b * H2 * W2 * C2);
+        }
         p.b2 = a.take<float>(b * H2 * W2 * C2);
         p.b3 = a.take<float>(b * H1 * W1 * C1);
         p.logits_p = a.take<float>(b * NPIX * 4);
@@ -254,13 +266,18 @@ static VaePlan make_plan(void* ws, int64_t ws_bytes, int B, int ct, int z, int m
     if (mode >= CPB_WS_TRAIN) {
         p.gA = a.take<float>(b * H1 * W1 * C1);
         p.gB = a.take<float>(b * H1 * W1 * C1);
-        p.gA_lo = a.take<float>(b * H1 * W1 * C1);
-        p.gB_lo = a.take<float>(b * H1 * W1 * C1);
+        if (need_lo) {
+            p.gA_lo = a.take<float>(b * H1 * W1 * C1);
+            p.gB_lo = a.take<float>(b * H1 * W1 * C1);
+        }
         p.gz = a.take<float>(b * z);
         p.gheads = a.take<float>(2 * b * z);
         p.partial = a.take<float>(max_partial_floats(B, z));
         p.colsum = a.take<float>(colsum_scratch_floats(b * NPIX, 4) + colsum_scratch_floats(b * H1 * W1, C1) +
                                  colsum_scratch_floats(b, FEAT));
+        p.cs_partial = a.take<float>(kColsumPartialFloats);
+        p.cs_edge = a.take<float>(edge_gather_blocks(B) * C1);
+        p.frame_dsum = a.take<float>(b * 4);
     }
     p.bytes = a.off;
     p.ok = ws == nullptr || !a.overflow;
@@ -374,13 +391,35 @@ static thread_local float* tl_lo_scratch = nullptr;   // lo plane of the current
 
 // src_lo / dst_lo: lo planes (x - trunc_tf32(x)) of the source (written by its producer; nullptr: computed here into the
 // scratch plane) and of the destination (written by the epilogue for the consuming layer; nullptr: not needed)
+// bias_out / cs_partial: when given and the layer runs on the tc2 kernel, the epilogue also produces the column sums of dst
+// (the bias gradient of the layer whose pre-activation gradient dst is) and *bias_done is set; otherwise the caller runs
+// launch_colsum on dst afterwards.
 static int32_t tg(const char* label, const TapGemmParams& p, cudaStream_t s, int scatter_k = 0,
-                  const float* src_lo = nullptr, float* dst_lo = nullptr) {
+                  const float* src_lo = nullptr, float* dst_lo = nullptr, float* bias_out = nullptr, float* cs_partial = nullptr,
+                  bool* bias_done = nullptr) {
+    if (bias_done != nullptr) *bias_done = false;
+    if (g_math_mode == 1 && p.wk_hi != nullptr && tl_lo_scratch != nullptr) {
+        TapGemmParams q = scatter_k > 0 ? quad_from_scatter(p, scatter_k) : p;
+        q.debug = tc_debug_flags();
+        if (tc2_tapgemm_supported(q, scatter_k)) {                                               // TMA tensor maps, no lo planes
+            const bool fold = bias_out != nullptr && cs_partial != nullptr && (long long)q.N * kTc2ColsumRows <= kColsumPartialFloats;
+            if (fold) {
+                CPB_CUDA(cudaMemsetAsync(cs_partial, 0, sizeof(float) * (size_t)q.N * kTc2ColsumRows, s));
+                q.colsum = cs_partial;
+            }
+            { ProfScope prof(label, s);
+              CPB_TRY(launch_tc2_tapgemm(q, scatter_k, s)); }
+            if (fold) {
+                CPB_TRY(launch_colsum_fold(cs_partial, kTc2ColsumRows, q.N, q.quad ? q.quad_cb : q.N, bias_out, s));
+                *bias_done = true;
+            }
+            return CPB_OK;
+        }
+    }
     ProfScope prof(label, s);
     if (g_math_mode == 1 && p.wk_hi != nullptr && tl_lo_scratch != nullptr) {
         TapGemmParams q = scatter_k > 0 ? quad_from_scatter(p, scatter_k) : p;
         q.debug = tc_debug_flags();
-        if (tc2_tapgemm_supported(q, scatter_k)) return launch_tc2_tapgemm(q, scatter_k, s);     // TMA tensor maps, no lo planes
         // with tc2 enabled the weight images are in the tc2 block order and the SIMT transposes are not written: a layer the
         // tc2 kernel cannot take must not silently run on stale operands (cannot happen with the fixed 80x160 geometry)
         CPB_REQUIRE(!tc2_enabled(), "layer %s is not supported by the tc2 tap-GEMM (C=%d, N=%d)", label, q.C, q.N);
@@ -604,7 +643,7 @@ static int32_t run_forward_loss(const VaePlan& pl, const VaeLayout& L, const cpb
     const float gscale = cfg->loss_scale / (float)B;
     { ProfScope prof("recon_loss", s);
       CPB_TRY(launch_recon_loss(pl.logits_p, yp, B, pl.ct, cfg->loss_type, gscale, pl.frame_loss,
-                                want_dlogits ? pl.logits_p : nullptr, s)); }
+                                want_dlogits ? pl.logits_p : nullptr, s, want_dlogits ? pl.frame_dsum : nullptr)); }
     return CPB_OK;
 }
 
@@ -622,29 +661,32 @@ static int32_t run_backward(const VaePlan& pl, const VaeLayout& L, const cpb_vae
       CPB_TRY(launch_edge_wgrad(dlog, pl.ct, pl.b3, B, pl.partial, s));
       CPB_TRY(launch_reduce_partials(pl.partial, edge_wgrad_ctas(B), 16 * pl.ct, C1, 16 * pl.ct, 16 * pl.ct,
                                      grads + L.off[T_DECONV4_K], s)); }
-    CPB_TRY(launch_colsum(dlog, (long long)B * NPIX, 4, pl.ct, grads + L.off[T_DECONV4_B], cs, s));
+    // the bias gradients of the two outermost layers come out of the kernels that write their pre-activation gradients
+    // (recon_loss: per-frame channel sums; edge_gather: per-CTA column sums) instead of separate passes over 0.8 + 1.6 GB
+    CPB_TRY(launch_colsum(pl.frame_dsum, B, 4, pl.ct, grads + L.off[T_DECONV4_B], cs, s));
     { ProfScope prof("deconv4.dgrad", s);
       CPB_TRY(launch_edge_gather(dlog, pl.ct, params + L.off[T_DECONV4_K], nullptr, pl.b3, pl.gA,
-                                 g_math_mode == 1 && !tc2_enabled() ? pl.gA_lo : nullptr, B, s)); }   // gA = g(b3 pre-activation)
+                                 g_math_mode == 1 && !tc2_enabled() ? pl.gA_lo : nullptr, B, s, pl.cs_edge)); }   // gA = g(b3 pre-activation)
     TapGemmParams p;
     // ---- deconv3
     CPB_TRY(run_wgrad("deconv3.wgrad", pl.gA, W1, C1, (long long)H1 * W1 * C1, 5, pl.b2, B, H2, W2, C2, 5 * 5 * C1, 5 * 5 * C1,
                       pl.partial, grads + L.off[T_DECONV3_K], s));
-    CPB_TRY(launch_colsum(pl.gA, (long long)B * H1 * W1, C1, C1, grads + L.off[T_DECONV3_B], cs, s));
+    CPB_TRY(launch_colsum(pl.cs_edge, edge_gather_blocks(B), C1, C1, grads + L.off[T_DECONV3_B], cs, s));
     p = gather_problem(pl.gA, B, H1, W1, C1, 5, params + L.off[T_DECONV3_K], C2, nullptr, pl.b2, pl.gB, 0,
                        pl.relayout + pl.rl.tc[TC_DECONV3].f_hi, pl.relayout + pl.rl.tc[TC_DECONV3].f_lo);
-    CPB_TRY(tg("deconv3.dgrad", p, s, 0, pl.gA_lo, pl.gB_lo));                                   // gB = g(b2)
+    bool bias_done = false;
+    CPB_TRY(tg("deconv3.dgrad", p, s, 0, pl.gA_lo, pl.gB_lo, grads + L.off[T_DECONV2_B], pl.cs_partial, &bias_done));   // gB = g(b2)
     // ---- deconv2
     CPB_TRY(run_wgrad("deconv2.wgrad", pl.gB, W2, C2, (long long)H2 * W2 * C2, 4, pl.b1, B, H3, W3, C3, 16 * C2, 16 * C2, pl.partial,
                       grads + L.off[T_DECONV2_K], s));
-    CPB_TRY(launch_colsum(pl.gB, (long long)B * H2 * W2, C2, C2, grads + L.off[T_DECONV2_B], cs, s));
+    if (!bias_done) CPB_TRY(launch_colsum(pl.gB, (long long)B * H2 * W2, C2, C2, grads + L.off[T_DECONV2_B], cs, s));
     p = gather_problem(pl.gB, B, H2, W2, C2, 4, params + L.off[T_DECONV2_K], C3, nullptr, pl.b1, pl.gA, 0,
                        pl.relayout + pl.rl.tc[TC_DECONV2].f_hi, pl.relayout + pl.rl.tc[TC_DECONV2].f_lo);
-    CPB_TRY(tg("deconv2.dgrad", p, s, 0, pl.gB_lo, pl.gA_lo));                                   // gA = g(b1)
+    CPB_TRY(tg("deconv2.dgrad", p, s, 0, pl.gB_lo, pl.gA_lo, grads + L.off[T_DECONV1_B], pl.cs_partial, &bias_done));   // gA = g(b1)
     // ---- deconv1
     CPB_TRY(run_wgrad("deconv1.wgrad", pl.gA, W3, C3, (long long)H3 * W3 * C3, 4, pl.d1, B, H4, W4, C4, 16 * C3, 16 * C3, pl.partial,
                       grads + L.off[T_DECONV1_K], s));
-    CPB_TRY(launch_colsum(pl.gA, (long long)B * H3 * W3, C3, C3, grads + L.off[T_DECONV1_B], cs, s));
+    if (!bias_done) CPB_TRY(launch_colsum(pl.gA, (long long)B * H3 * W3, C3, C3, grads + L.off[T_DECONV1_B], cs, s));
     p = gather_problem(pl.gA, B, H3, W3, C3, 4, params + L.off[T_DECONV1_K], C4, nullptr, nullptr, pl.gB, 0,
                        pl.relayout + pl.rl.tc[TC_DECONV1].f_hi, pl.relayout + pl.rl.tc[TC_DECONV1].f_lo);
     CPB_TRY(tg("deconv1.dgrad", p, s, 0, pl.gA_lo, nullptr));                                   // gB = g(d1) [B, 6144]
@@ -677,26 +719,26 @@ static int32_t run_backward(const VaePlan& pl, const VaeLayout& L, const cpb_vae
     CPB_TRY(launch_colsum(pl.gA, (long long)B * H4 * W4, C4, C4, grads + L.off[T_CONV4_B], cs, s));
     p = scatter_problem(pl.gA, B, H4, W4, C4, 4, pl.relayout + pl.rl.conv4T, C3, nullptr, pl.a3, pl.gB, H3, W3, 0,
                         pl.relayout + pl.rl.tc[TC_CONV4].t_hi, pl.relayout + pl.rl.tc[TC_CONV4].t_lo);
-    CPB_TRY(tg("conv4.dgrad", p, s, 4, nullptr, pl.gB_lo));                                   // gB = g(a3)
+    CPB_TRY(tg("conv4.dgrad", p, s, 4, nullptr, pl.gB_lo, grads + L.off[T_CONV3_B], pl.cs_partial, &bias_done));   // gB = g(a3)
     // ---- conv3
     CPB_TRY(run_wgrad("conv3.wgrad", pl.a2, W2, C2, (long long)H2 * W2 * C2, 4, pl.gB, B, H3, W3, C3, 16 * C2, 16 * C2, pl.partial,
                       grads + L.off[T_CONV3_K], s));
-    CPB_TRY(launch_colsum(pl.gB, (long long)B * H3 * W3, C3, C3, grads + L.off[T_CONV3_B], cs, s));
+    if (!bias_done) CPB_TRY(launch_colsum(pl.gB, (long long)B * H3 * W3, C3, C3, grads + L.off[T_CONV3_B], cs, s));
     p = scatter_problem(pl.gB, B, H3, W3, C3, 4, pl.relayout + pl.rl.conv3T, C2, nullptr, pl.a2, pl.gA, H2, W2, 0,
                         pl.relayout + pl.rl.tc[TC_CONV3].t_hi, pl.relayout + pl.rl.tc[TC_CONV3].t_lo);
-    CPB_TRY(tg("conv3.dgrad", p, s, 4, pl.gB_lo, pl.gA_lo));                                   // gA = g(a2)
+    CPB_TRY(tg("conv3.dgrad", p, s, 4, pl.gB_lo, pl.gA_lo, grads + L.off[T_CONV2_B], pl.cs_partial, &bias_done));   // gA = g(a2)
     // ---- conv2
     CPB_TRY(run_wgrad("conv2.wgrad", pl.a1, W1, C1, (long long)H1 * W1 * C1, 4, pl.gA, B, H2, W2, C2, 16 * C1, 16 * C1, pl.partial,
                       grads + L.off[T_CONV2_K], s));
-    CPB_TRY(launch_colsum(pl.gA, (long long)B * H2 * W2, C2, C2, grads + L.off[T_CONV2_B], cs, s));
+    if (!bias_done) CPB_TRY(launch_colsum(pl.gA, (long long)B * H2 * W2, C2, C2, grads + L.off[T_CONV2_B], cs, s));
     p = scatter_problem(pl.gA, B, H2, W2, C2, 4, pl.relayout + pl.rl.conv2T, C1, nullptr, pl.a1, pl.gB, H1, W1, 0,
                         pl.relayout + pl.rl.tc[TC_CONV2].t_hi, pl.relayout + pl.rl.tc[TC_CONV2].t_lo);
-    CPB_TRY(tg("conv2.dgrad", p, s, 4, pl.gA_lo, nullptr));                                   // gB = g(a1)
+    CPB_TRY(tg("conv2.dgrad", p, s, 4, pl.gA_lo, nullptr, grads + L.off[T_CONV1_B], pl.cs_partial, &bias_done));   // gB = g(a1)
     // ---- conv1 (its input gradient is never used: the reference computes and discards it)
     { ProfScope prof("conv1.wgrad", s);
       CPB_TRY(launch_edge_wgrad(pl.xp, 3, pl.gB, B, pl.partial, s));
       CPB_TRY(launch_reduce_partials(pl.partial, edge_wgrad_ctas(B), 48, C1, 48, 48, grads + L.off[T_CONV1_K], s)); }
-    CPB_TRY(launch_colsum(pl.gB, (long long)B * H1 * W1, C1, C1, grads + L.off[T_CONV1_B], cs, s));
+    if (!bias_done) CPB_TRY(launch_colsum(pl.gB, (long long)B * H1 * W1, C1, C1, grads + L.off[T_CONV1_B], cs, s));
     return CPB_OK;
 }
 
