@@ -347,10 +347,16 @@ __global__ void colsum_fold_kernel(const float* __restrict__ partial, int rows, 
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (c >= cb) return;
-    float s = 0.f;
-    for (int r = lane; r < rows; r += 32)
-        for (int k = c; k < N; k += cb) s += partial[(long long)r * N + k];
-    s = warp_sum(s);
+    // rows % 128 == 0 (kTc2ColsumRows): 4 independent accumulators keep 4+ loads in flight per lane
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    for (int r = lane; r + 96 < rows; r += 128)
+        for (int k = c; k < N; k += cb) {
+            s0 += partial[(long long)r * N + k];
+            s1 += partial[(long long)(r + 32) * N + k];
+            s2 += partial[(long long)(r + 64) * N + k];
+            s3 += partial[(long long)(r + 96) * N + k];
+        }
+    float s = warp_sum((s0 + s1) + (s2 + s3));
     if (lane == 0) out[c] = s;
 }
 
@@ -539,7 +545,7 @@ long long colsum_scratch_floats(long long rows, int pitch) {
 }
 
 int32_t launch_colsum_fold(const float* partial, int rows, int N, int cb, float* out, cudaStream_t stream) {
-    CPB_REQUIRE(cb > 0 && N % cb == 0, "colsum_fold: N must be a multiple of the channel count");
+    CPB_REQUIRE(cb > 0 && N % cb == 0 && rows % 128 == 0, "colsum_fold: N must be a multiple of the channel count, rows of 128");
     ProfScope prof("bias_grad.colsum", stream);
     colsum_fold_kernel<<<cdiv(cb, 8), 256, 0, stream>>>(partial, rows, N, cb, out);
     CPB_LAUNCHED();

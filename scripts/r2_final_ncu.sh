@@ -8,6 +8,6 @@ wc -l gpurun_out/r2_launches.csv
 timeout 1200 ncu --set full --import-source on --clock-control none -k regex:"tc2_tapgemm_kernel|tc_wgrad_kernel" --launch-skip 18 -c 18 \
     -o gpurun_out/r2_full_tc -f python scripts/tc_prof.py > gpurun_out/r2_ncu_full_tc.log 2>&1
 ncu -i gpurun_out/r2_full_tc.ncu-rep --page raw --csv > gpurun_out/r2_ncu_full_raw_tc.csv 2>/dev/null; wc -l gpurun_out/r2_ncu_full_raw_tc.csv
-timeout 900 ncu --set full --clock-control none -k regex:"edge_|deconv4_fwd|recon_loss|colsum_kernel|prep_frames|adam_kernel" --launch-skip 40 -c 30 \
+timeout 900 ncu --set full --clock-control none -k regex:"edge_|deconv4_fwd|recon_loss|colsum_kernel|prep_frames|adam_kernel" --launch-skip 18 -c 22 \
     -o gpurun_out/r2_full_other -f python scripts/tc_prof.py > gpurun_out/r2_ncu_full_other.log 2>&1
 ncu -i gpurun_out/r2_full_other.ncu-rep --page raw --csv > gpurun_out/r2_ncu_full_raw_other.csv 2>/dev/null; wc -l gpurun_out/r2_ncu_full_raw_other.csv
