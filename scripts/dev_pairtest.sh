@@ -1,4 +1,6 @@
 mkdir -p gpurun_out
-timeout 200 python -m pytest tests/test_vae_gpu.py tests/test_vae_large_gpu.py -x -q > gpurun_out/p13_vae.txt 2>&1; tail -4 gpurun_out/p13_vae.txt
-B=4096 timeout 100 python scripts/step_profile.py > gpurun_out/p13_step_B4096.txt 2>&1; head -36 gpurun_out/p13_step_B4096.txt
-B=512 timeout 100 python scripts/step_profile.py > gpurun_out/p13_step_B512.txt 2>&1; head -3 gpurun_out/p13_step_B512.txt
+export WEIGHTS=shipped
+FRAMES=shipped SEED=0 B=4 timeout 100 python scripts/diag_smoke.py > gpurun_out/d5.txt 2>&1; grep -v Warning gpurun_out/d5.txt | tail -23 | cut -c1-80
+CPB_TC_PAIR=0 FRAMES=shipped SEED=0 B=4 timeout 100 python scripts/diag_smoke.py > gpurun_out/d6.txt 2>&1; tail -23 gpurun_out/d6.txt | cut -c1-80
+SEED=0 B=4 timeout 100 python scripts/diag_smoke.py > gpurun_out/d7.txt 2>&1; tail -23 gpurun_out/d7.txt | cut -c1-80 | head -5
+FRAMES=shipped SEED=8 B=8 timeout 100 python scripts/diag_smoke.py > gpurun_out/d8.txt 2>&1; tail -23 gpurun_out/d8.txt | cut -c1-80 | head -5
