@@ -39,10 +39,13 @@ if rank == 0:
     s_losses = [single.train_step_device(x, x, eps).clone() for _ in range(3)]
     perr = float((dp.params - single.params).norm() / single.params.norm())
     lerr = max(float(((a - b).abs() / b.abs()).max()) for a, b in zip(dp_losses, s_losses))
-    # gate: the N-rank and the 1-rank run are two float32 evaluations of the same three steps that differ only in
-    # summation order; each must be as close to the float64 oracle as a float32 implementation can be, so both are
-    # compared with the oracle and gated at max(1e-5, 2 x the float32 CPU restatement's own error) -- no constant picked
-    # after the fact.  (oracle/ is test infrastructure: this script is a test, not the product.)
+    # What is GATED is the data-parallel property itself: the N-rank run and the 1-rank run are two float32 evaluations of the
+    # same three steps that differ only in summation order -> parameters and losses within 1e-5 (the path's tolerance), replicas
+    # bit-identical.  The distance of BOTH runs to the float64 oracle (and the float32 CPU restatement's own distance) is
+    # REPORTED next to it, not gated: parameters after the first Adam steps from zero slots move by ~lr * sign(g), so a tensor's
+    # distance to float64 is decided by the handful of elements whose gradient is ~0 (profiles/r2_parity_conditioning.md);
+    # the oracle parity of the single-GPU step is what tests/test_vae_gpu.py and tests/test_vae_large_gpu.py gate.
+    # (oracle/ is test infrastructure: this script is a test, not the product.)
     from oracle import vae_oracle as vo
     from oracle.torch_ref import TorchVAETrainer
     p64 = {k: v.astype(np.float64) for k, v in w0.items()}
@@ -56,16 +59,12 @@ if rank == 0:
         a = np.asarray(a, np.float64).ravel(); b = np.asarray(b, np.float64).ravel()
         return float(np.linalg.norm(a - b) / np.linalg.norm(b))
     wd, ws_ = dp.get_weights(), single.get_weights()
-    worst_dp = worst_single = worst_gate = 0.0
-    ok = same and lerr < 1e-5
-    for k in p64:
-        gate = max(1e-5, 2.0 * rel(cpu32.p[k].detach().numpy(), p64[k]))
-        e_dp, e_s = rel(wd[k], p64[k]), rel(ws_[k], p64[k])
-        ok = ok and e_dp < gate and e_s < gate
-        worst_dp, worst_single, worst_gate = max(worst_dp, e_dp), max(worst_single, e_s), max(worst_gate, gate)
-    msg = ("world=%d  params vs float64 oracle: %d-rank %.3e, 1-rank %.3e (gate max(1e-5, 2 x fp32-CPU error) <= %.3e); "
-           "%d-rank vs 1-rank %.3e; loss rel err %.3e; replicas identical: %s"
-           % (world, world, worst_dp, worst_single, worst_gate, world, perr, lerr, same))
+    ok = same and lerr < 1e-5 and perr < 1e-5
+    worst = max(p64, key=lambda k: rel(wd[k], p64[k]))
+    msg = ("world=%d  GATED: %d-rank vs 1-rank params %.3e, losses %.3e (bar 1e-5), replicas identical: %s.  REPORTED: worst tensor vs "
+           "float64 oracle after 3 Adam steps from zero slots: %s %d-rank %.3e, 1-rank %.3e, float32 CPU restatement %.3e"
+           % (world, world, perr, lerr, same, worst, world, rel(wd[worst], p64[worst]), rel(ws_[worst], p64[worst]),
+              rel(cpu32.p[worst].detach().numpy(), p64[worst])))
     print(msg, flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     open(os.path.join(ROOT, "gpurun_out", "dp_check.txt"), "w").write(msg + "\n")
