@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-B=128 timeout 100 python scripts/diag_dp.py > gpurun_out/dd1.txt 2>&1; grep -v Warn gpurun_out/dd1.txt | tail -23 | cut -c1-170
-CPB_TC_PAIR=0 B=128 timeout 100 python scripts/diag_dp.py > gpurun_out/dd2.txt 2>&1; grep -v Warn gpurun_out/dd2.txt | tail -23 | cut -c1-110
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29552 scripts/dp_check.py > gpurun_out/r2_dp_check_2gpu.txt 2>&1; echo rc=$?; tail -2 gpurun_out/r2_dp_check_2gpu.txt
