@@ -118,12 +118,17 @@ edge_gather_kernel(const float4* __restrict__ big4, const float* __restrict__ w,
 #pragma unroll
         for (int j = 0; j < SC / 2; ++j) csred[threadIdx.x * 17 + j] = csum[j];
         __syncthreads();
-        if (threadIdx.x < SC) {
-            const int c = threadIdx.x, par = (c >> 2) & 1, li = (c >> 3) * 4 + (c & 3);
+        // two stages (16 + 4 terms per chain instead of one 64-term chain at the tail of every CTA), fixed order
+        __shared__ float csq[4][SC];
+        {
+            const int c = threadIdx.x & (SC - 1), qd = threadIdx.x >> 5, par = (c >> 2) & 1, li = (c >> 3) * 4 + (c & 3);
             float a = 0.f;
-            for (int th = par; th < 128; th += 2) a += csred[th * 17 + li];
-            cs_partial[(long long)blockIdx.x * SC + c] = a;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) a += csred[(qd * 32 + par + 2 * k) * 17 + li];
+            csq[qd][c] = a;
         }
+        __syncthreads();
+        if (threadIdx.x < SC) cs_partial[(long long)blockIdx.x * SC + threadIdx.x] = (csq[0][threadIdx.x] + csq[1][threadIdx.x]) + (csq[2][threadIdx.x] + csq[3][threadIdx.x]);
     }
 }
 

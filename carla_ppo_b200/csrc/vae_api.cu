@@ -1050,11 +1050,21 @@ int32_t cpb_vae_layout(int32_t ct, int32_t z, int64_t* offsets, int64_t* sizes, 
     return CPB_OK;
 }
 
+// The plan depends on which kernel family this device will run (the tc2 kernels need no lo planes): initialise first when a
+// device is usable, so that the size handed out is the size the calls will use.  Without a device (symbol / layout checks
+// on a CPU-only host) the query stays conservative.
+static void init_if_device_present() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) == cudaSuccess && n > 0) (void)cpb::ensure_init();
+    else (void)cudaGetLastError();
+}
+
 int64_t cpb_vae_workspace_bytes(int32_t batch, int32_t ct, int32_t z, int32_t mode) {
     if (batch < 1 || (ct != 1 && ct != 3) || z < 64 || z % 64 != 0 || mode < 0 || mode > 2) {
         cpb::set_error("cpb_vae_workspace_bytes: bad arguments");
         return CPB_ERR_INVALID_ARGUMENT;
     }
+    init_if_device_present();
     return make_plan(nullptr, 0, batch, ct, z, mode).bytes;
 }
 
