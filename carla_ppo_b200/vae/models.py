@@ -188,7 +188,9 @@ class VAE:
         _lib.check(lib.cpb_vae_layout(self.target_shape[2], self.z_dim, offs, sizes, shapes, C.byref(total)), "cpb_vae_layout")
 
     def _workspace_need(self, batch, mode):
-        return self._libh.cpb_vae_workspace_bytes(batch, self.target_shape[2], self.z_dim, mode)
+        # on this instance's device: the size query initialises the library there (the plan depends on the kernel family)
+        with self._on_device():
+            return self._libh.cpb_vae_workspace_bytes(batch, self.target_shape[2], self.z_dim, mode)
 
     def _initial_weights(self) -> Dict[str, np.ndarray]:
         rng = np.random.RandomState(self._seed if self._seed is not None else np.random.randint(0, 2 ** 31 - 1))
